@@ -1,0 +1,44 @@
+"""Build game_of_flies_b200/csrc/libgof_b200.so for sm_100a with nvcc (in-tree).
+
+nvcc cross-compiles without a GPU, so this runs in the CPU-only build container
+and the resulting .so travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libgof_b200.so")
+SOURCES = [os.path.join(CSRC, "gof_b200.cu")]
+HEADERS = [os.path.join(CSRC, f) for f in ("gof_kernels.cuh", "gof_binning.cuh", "gof_force.cuh")]
+HEADERS.append(os.path.join(os.path.dirname(HERE), "include", "gof_b200.h"))
+
+def nvcc_path() -> str:
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return LIB
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+             "-shared", "-Xcompiler", "-fPIC"]
+    if verbose:
+        flags += ["-Xptxas", "-v"]
+    cmd = [nvcc_path(), *flags, *SOURCES, "-o", LIB]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

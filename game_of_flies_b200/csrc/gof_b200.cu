@@ -1,0 +1,931 @@
+// gof_b200.cu -- C ABI (include/gof_b200.h) of the B200-native Game_of_Flies engine.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared
+//        -Xcompiler -fPIC  (see game_of_flies_b200/build.py)
+//
+// The host code below only sequences kernel launches and carves caller-provided
+// device memory; every number a user sees is produced by the kernels in
+// gof_binning.cuh / gof_force.cuh and the small element-wise kernels here.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gof_b200.h"
+#include "gof_force.cuh"
+
+using namespace gof;
+
+// --------------------------------------------------------------------------------------
+// errors, launch accounting
+// --------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define GOF_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t err__ = (expr);                                                           \
+        if (err__ != cudaSuccess)                                                             \
+            return fail((int)err__, std::string(#expr) + ": " + cudaGetErrorString(err__));   \
+    } while (0)
+
+#define GOF_LAUNCH(kernel, grid, block, smem, stream, ...)                                    \
+    do {                                                                                      \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                           \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+        cudaError_t err__ = cudaGetLastError();                                               \
+        if (err__ != cudaSuccess)                                                             \
+            return fail((int)err__, std::string(#kernel) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+extern "C" int gof_abi_version(void) { return GOF_ABI_VERSION; }
+extern "C" const char* gof_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint64_t gof_launch_count(void) { return g_launches.load(); }
+extern "C" void gof_reset_launch_count(void) { g_launches.store(0); }
+extern "C" int gof_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// --------------------------------------------------------------------------------------
+// host-side geometry (reference main/simulation.py:103-139)
+// --------------------------------------------------------------------------------------
+extern "C" int gof_grid_init(gof_grid* grid, double limit_x, double limit_y, double limit_z,
+                             double r_max)
+{
+    if (!grid || !(r_max > 0) || !(limit_x > 0) || !(limit_y > 0) || limit_z < 0)
+        return fail(GOF_E_INVALID, "gof_grid_init: bad limits or r_max");
+    grid->limit_x = limit_x;
+    grid->limit_y = limit_y;
+    grid->limit_z = limit_z;
+    grid->r_max = r_max;
+    grid->num_bin_x = (int)std::floor(limit_x / r_max);
+    grid->num_bin_y = (int)std::floor(limit_y / r_max);
+    grid->num_bin_z = limit_z != 0 ? (int)std::floor(limit_z / r_max) : 0;
+    if (grid->num_bin_x < 1 || grid->num_bin_y < 1 || (limit_z != 0 && grid->num_bin_z < 1))
+        return fail(GOF_E_GRID, "gof_grid_init: r_max larger than the box");
+    grid->bin_size_x = limit_x / grid->num_bin_x;
+    grid->bin_size_y = limit_y / grid->num_bin_y;
+    grid->bin_size_z = limit_z != 0 ? limit_z / grid->num_bin_z : 0.0;
+    grid->num_cells = grid->num_bin_x * grid->num_bin_y * (grid->num_bin_z > 0 ? grid->num_bin_z : 1);
+    if (grid->num_bin_x < 3 || grid->num_bin_y < 3 || (limit_z != 0 && grid->num_bin_z < 3))
+        return fail(GOF_E_GRID,
+                    "fewer than 3 bins along an axis: the reference assumes r_max < min(limits) / 3 "
+                    "(acceleration_updater.py:302)");
+    return 0;
+}
+
+extern "C" int gof_set_bin_neighbours(int nbx, int nby, int nbz, int32_t* out)
+{
+    if (!out || nbx < 1 || nby < 1) return fail(GOF_E_INVALID, "gof_set_bin_neighbours: bad arguments");
+    auto wrap = [](int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); };
+    // offsets of the half stencil, in the order of the reference table
+    static const int o2[5][2] = {{0, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
+    static const int o3[9][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}, {0, 0}};
+    const int width = nbz < 1 ? 5 : 14;
+    const int layers = nbz < 1 ? 1 : nbz;
+    for (int k = 0; k < layers; ++k)
+        for (int j = 0; j < nby; ++j)
+            for (int i = 0; i < nbx; ++i) {
+                int32_t* row = out + (size_t)(i + nbx * (j + nby * k)) * width;
+                for (int q = 0; q < 5; ++q)
+                    row[q] = wrap(i + o2[q][0], nbx) + nbx * (wrap(j + o2[q][1], nby) + nby * k);
+                if (nbz >= 1) {
+                    const int kp = wrap(k + 1, nbz);
+                    for (int q = 0; q < 9; ++q)
+                        row[5 + q] = wrap(i + o3[q][0], nbx) + nbx * (wrap(j + o3[q][1], nby) + nby * kp);
+                }
+            }
+    return 0;
+}
+
+static float next_down(float v) { return std::nextafterf(v, -INFINITY); }
+static float next_up(float v) { return std::nextafterf(v, INFINITY); }
+
+// local_layers == 0: the engine holds the whole periodic box.
+static int make_geometry(const gof_grid* grid, int layer_base, int local_layers, Geometry* out)
+{
+    if (!grid) return fail(GOF_E_INVALID, "null grid");
+    const bool is3d = grid->num_bin_z > 0;
+    if (grid->num_bin_x < 3 || grid->num_bin_y < 3 || (is3d && grid->num_bin_z < 3))
+        return fail(GOF_E_GRID, "fewer than 3 bins along an axis (reference assumes r_max < min(limits) / 3)");
+    if (is3d && !(grid->bin_size_z > 1.0))
+        return fail(GOF_E_GRID, "3D box with bin_size_z <= 1: the reference bins such a box as 2D "
+                                "(acceleration_updater.py:54); refuse instead of diverging");
+    Geometry g{};
+    g.nbx = grid->num_bin_x;
+    g.nby = grid->num_bin_y;
+    g.nbz = is3d ? grid->num_bin_z : 0;
+    g.is3d = is3d;
+    if (local_layers > 0) {
+        g.nlz = local_layers;
+        g.layer_base = layer_base;
+        g.index_wrap_z = 0;
+    } else {
+        g.nlz = is3d ? grid->num_bin_z : 1;
+        g.layer_base = 0;
+        g.index_wrap_z = 1;
+    }
+    g.num_cells = g.nbx * g.nby * g.nlz;
+    g.bsx = grid->bin_size_x;
+    g.bsy = grid->bin_size_y;
+    g.bsz = grid->bin_size_z;
+    g.Lxd = grid->limit_x;
+    g.Lyd = grid->limit_y;
+    g.Lzd = grid->limit_z;
+    g.rmaxd = grid->r_max;
+    g.r2d = grid->r_max * grid->r_max;
+    g.Lx = (float)g.Lxd;
+    g.Ly = (float)g.Lyd;
+    g.Lz = (float)g.Lzd;
+    g.rmax = (float)g.rmaxd;
+    // Guard band: the fp32 squared distance of a pair whose true distance is r_max can be
+    // off by the rounding of the shifted coordinate (<= ulp(L + r_max)), the rounding of
+    // the difference and of the three squares.  Inside the band the kernel decides in fp64.
+    const double lmax = std::fmax(g.Lxd, std::fmax(g.Lyd, g.Lzd)) + g.rmaxd;
+    const double ulp = (double)next_up((float)lmax) - (double)(float)lmax;
+    const double band = 2.0 * std::sqrt(3.0) * g.rmaxd * (3.0 * ulp) + 32.0 * 1.1920929e-7 * g.r2d;
+    g.r2_lo = next_down((float)(g.r2d - band));
+    g.r2_hi = next_up((float)(g.r2d + band));
+    *out = g;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// species table
+// --------------------------------------------------------------------------------------
+struct HostSpecies {
+    int T = 0;
+    bool has_boids = false;
+    std::vector<PairParam> table;
+    std::vector<unsigned> kind_rows;
+    std::vector<double> sep_exact;
+    std::vector<int> self_kind;
+    size_t bytes() const
+    {
+        return align_up(table.size() * sizeof(PairParam)) + align_up(kind_rows.size() * sizeof(unsigned)) +
+               align_up(sep_exact.size() * sizeof(double)) + align_up(self_kind.size() * sizeof(int));
+    }
+};
+
+struct DeviceSpecies {
+    PairParam* table;
+    unsigned* kind_rows;
+    double* sep_exact;
+    int* self_kind;
+};
+
+static size_t species_bytes(int T)
+{
+    return align_up((size_t)T * T * sizeof(PairParam)) + align_up(T * sizeof(unsigned)) +
+           align_up((size_t)T * T * sizeof(double)) + align_up(T * sizeof(int));
+}
+
+// parameter_matrix: float64 [5][T][T] as built by Simulation.__init__ (simulation.py:54-98).
+static int build_species(const double* pm, int T, HostSpecies* out)
+{
+    if (!pm || T < 1 || T > GOF_MAX_TYPES) return fail(GOF_E_INVALID, "num_types must be in [1, 16]");
+    out->T = T;
+    out->has_boids = false;
+    out->table.assign((size_t)T * T, PairParam{});
+    out->kind_rows.assign(T, 0u);
+    out->sep_exact.assign((size_t)T * T, 0.0);
+    out->self_kind.assign(T, 0);
+    const int TT = T * T;
+    for (int i = 0; i < T; ++i)
+        for (int j = 0; j < T; ++j) {
+            const int q = i * T + j;
+            const double a0 = pm[0 * TT + q], a1 = pm[1 * TT + q], a2 = pm[2 * TT + q], a3 = pm[3 * TT + q];
+            const double kind = pm[4 * TT + q];
+            PairParam p{};
+            if (kind == 1.0) {
+                out->has_boids = true;
+                out->kind_rows[i] |= 1u << j;
+                p.a = make_float4((float)(a0 / 5), (float)a1, (float)a2, (float)a3);
+                p.b = make_float4(0.f, 0.f, 0.f, 0.f);
+                out->sep_exact[q] = a0 / 5;
+            } else if (kind == 0.0) {
+                // clusters(): r_min, r_max, f_min, f_max
+                const double s1 = 2 * a3 / (a1 - a0);
+                p.a = make_float4((float)a0, (float)(a2 / a0), (float)a2, (float)((a0 + a1) / 2));
+                // f_tri(d) = s1 * min(d - r_min, r_max - d) = s1 * ((r_max - r_min)/2 - |d - mid|)
+                p.b = make_float4((float)s1, (float)(s1 * (a1 - a0) / 2), 0.f, 0.f);
+            } else {
+                // the reference ignores any other value (neither branch of lines 339 / 350 fires)
+                p.a = make_float4(-1.f, 0.f, 0.f, 0.f);
+                p.b = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            out->table[q] = p;
+            if (i == j) out->self_kind[i] = (kind == 0.0) ? 0 : 1;
+        }
+    return 0;
+}
+
+static DeviceSpecies carve_species(char* base, int T)
+{
+    DeviceSpecies d;
+    d.table = reinterpret_cast<PairParam*>(base);
+    base += align_up((size_t)T * T * sizeof(PairParam));
+    d.kind_rows = reinterpret_cast<unsigned*>(base);
+    base += align_up(T * sizeof(unsigned));
+    d.sep_exact = reinterpret_cast<double*>(base);
+    base += align_up((size_t)T * T * sizeof(double));
+    d.self_kind = reinterpret_cast<int*>(base);
+    return d;
+}
+
+static int upload_species(const HostSpecies& h, const DeviceSpecies& d, cudaStream_t st)
+{
+    // pageable sources: the runtime stages them before returning, so the vectors may change afterwards
+    GOF_CUDA(cudaMemcpyAsync(d.table, h.table.data(), h.table.size() * sizeof(PairParam), cudaMemcpyHostToDevice, st));
+    GOF_CUDA(cudaMemcpyAsync(d.kind_rows, h.kind_rows.data(), h.kind_rows.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    GOF_CUDA(cudaMemcpyAsync(d.sep_exact, h.sep_exact.data(), h.sep_exact.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    GOF_CUDA(cudaMemcpyAsync(d.self_kind, h.self_kind.data(), h.self_kind.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+static size_t force_smem_bytes(int T, bool boids)
+{
+    return (size_t)T * T * sizeof(PairParam) + (boids ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0);
+}
+
+template <bool BOIDS, int MODE>
+static int launch_force_t(const Geometry& g, const ForceArgs& a, cudaStream_t st)
+{
+    const size_t smem = force_smem_bytes(a.T, BOIDS);
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        GOF_CUDA(cudaFuncSetAttribute(k_force<BOIDS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    GOF_LAUNCH((k_force<BOIDS, MODE>), cdiv(a.home_count, kForceThreads), kForceThreads, smem, st, g, a);
+    return 0;
+}
+
+static int launch_force(const Geometry& g, const ForceArgs& a, bool boids, int mode, cudaStream_t st)
+{
+    if (a.home_count <= 0) return 0;
+    if (mode == kModeIntegrate)
+        return boids ? launch_force_t<true, kModeIntegrate>(g, a, st) : launch_force_t<false, kModeIntegrate>(g, a, st);
+    return boids ? launch_force_t<true, kModeScatter>(g, a, st) : launch_force_t<false, kModeScatter>(g, a, st);
+}
+
+// exclusive scan of m ints; tile_sums needs cdiv(m, kScanTile) ints
+static int launch_scan(const int* in, int m, int* tile_sums, int* out, cudaStream_t st)
+{
+    const int tiles = cdiv(m, kScanTile);
+    if (tiles <= 1) {
+        GOF_LAUNCH(k_scan_apply, 1, kScanThreads, 0, st, in, m, (const int*)nullptr, out);
+        return 0;
+    }
+    GOF_LAUNCH(k_scan_tile_sums, tiles, kScanThreads, 0, st, in, m, tile_sums);
+    GOF_LAUNCH(k_scan_tile_prefix, 1, kScanThreads, 0, st, tile_sums, tiles);
+    GOF_LAUNCH(k_scan_apply, tiles, kScanThreads, 0, st, in, m, (const int*)tile_sums, out);
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// small element-wise kernels
+// --------------------------------------------------------------------------------------
+namespace gof {
+
+constexpr int kEwThreads = 256;
+
+// integrator.step1 on SoA arrays (main/integrator.py:33-55)
+__global__ void __launch_bounds__(kEwThreads)
+k_step1(float* __restrict__ vx, float* __restrict__ vy, float* __restrict__ vz,
+        const float* __restrict__ ax, const float* __restrict__ ay, const float* __restrict__ az,
+        int n, float dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float h = 0.5f * dt;
+    float x = fmaf(ax[i], h, vx[i]), y = fmaf(ay[i], h, vy[i]), z = fmaf(az[i], h, vz[i]);
+    const float sq = x * x + y * y + z * z;
+    if (sq > kMaxSpeed * kMaxSpeed) {
+        const float k = kMaxSpeed / sqrtf(sq);
+        x *= k; y *= k; z *= k;
+    }
+    vx[i] = x; vy[i] = y; vz[i] = z;
+}
+
+// integrator.step2 on SoA arrays (main/integrator.py:58-88)
+__global__ void __launch_bounds__(kEwThreads)
+k_step2(float* __restrict__ px, float* __restrict__ py, float* __restrict__ pz,
+        float* __restrict__ vx, float* __restrict__ vy, float* __restrict__ vz,
+        const float* __restrict__ ax, const float* __restrict__ ay, const float* __restrict__ az,
+        const int* __restrict__ tia, const int* __restrict__ self_kind, int n, float dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a0 = ax[i], a1 = ay[i], a2 = az[i];
+    float v0 = vx[i], v1 = vy[i], v2 = vz[i];
+    px[i] += (v0 + 0.5f * a0 * dt) * dt;
+    py[i] += (v1 + 0.5f * a1 * dt) * dt;
+    pz[i] += (v2 + 0.5f * a2 * dt) * dt;
+    v0 = fmaf(a0, 0.5f * dt, v0);
+    v1 = fmaf(a1, 0.5f * dt, v1);
+    v2 = fmaf(a2, 0.5f * dt, v2);
+    if (self_kind[tia[i]] == 0) { v0 *= kDamping; v1 *= kDamping; v2 *= kDamping; }
+    vx[i] = v0; vy[i] = v1; vz[i] = v2;
+}
+
+// integrator.boundary_condition (main/integrator.py:91-114)
+__global__ void __launch_bounds__(kEwThreads)
+k_boundary(float* __restrict__ px, float* __restrict__ py, float* __restrict__ pz, float Lx,
+           float Ly, float Lz, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = px[i], y = py[i], z = pz[i];
+    if (x < 0.0f) x += Lx; else if (x > Lx) x -= Lx;
+    if (y < 0.0f) y += Ly; else if (y > Ly) y -= Ly;
+    if (z < 0.0f) z += Lz; else if (z > Lz) z -= Lz;
+    px[i] = x; py[i] = y; pz[i] = z;
+}
+
+// set_sq_speed + max_reduction (main/integrator.py:20-30, 117-129): grid-stride, one atomic per warp
+__global__ void __launch_bounds__(kEwThreads)
+k_max_sq_speed(const float* __restrict__ vx, const float* __restrict__ vy,
+               const float* __restrict__ vz, int n, unsigned* __restrict__ out_bits)
+{
+    float m = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float s = vx[i] * vx[i] + vy[i] * vy[i] + vz[i] * vz[i];
+        m = fmaxf(m, s);
+    }
+    const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if (lane_id() == 0) atomicMax(out_bits, w);
+}
+
+// SoA (particle order) -> engine float4 state; also the maximum squared speed of the upload
+__global__ void __launch_bounds__(kEwThreads)
+k_pack(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
+       const float* __restrict__ vx, const float* __restrict__ vy, const float* __restrict__ vz,
+       const float* __restrict__ ax, const float* __restrict__ ay, const float* __restrict__ az,
+       const int* __restrict__ types, int n, float4* __restrict__ posw, float4* __restrict__ veli,
+       float4* __restrict__ acc, unsigned* __restrict__ max_bits)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.0f;
+    if (i < n) {
+        const float4 v = make_float4(vx ? vx[i] : 0.f, vy ? vy[i] : 0.f, vz ? vz[i] : 0.f, __int_as_float(i));
+        posw[i] = make_float4(px[i], py[i], pz[i], __int_as_float(types[i]));
+        veli[i] = v;
+        acc[i] = make_float4(ax ? ax[i] : 0.f, ay ? ay[i] : 0.f, az ? az[i] : 0.f, 0.f);
+        sq = v.x * v.x + v.y * v.y + v.z * v.z;
+    }
+    const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(sq));
+    if (lane_id() == 0) atomicMax(max_bits, w);
+}
+
+// engine float4 state (cell order) -> SoA in particle order; null outputs are skipped
+__global__ void __launch_bounds__(kEwThreads)
+k_unpack(const float4* __restrict__ posw, const float4* __restrict__ veli,
+         const float4* __restrict__ acc, int n, float* __restrict__ px, float* __restrict__ py,
+         float* __restrict__ pz, float* __restrict__ vx, float* __restrict__ vy,
+         float* __restrict__ vz, float* __restrict__ ax, float* __restrict__ ay,
+         float* __restrict__ az)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 v = veli[k];
+    const int id = __float_as_int(v.w);
+    if (px) { const float4 p = posw[k]; px[id] = p.x; py[id] = p.y; pz[id] = p.z; }
+    if (vx) { vx[id] = v.x; vy[id] = v.y; vz[id] = v.z; }
+    if (ax) { const float4 a = acc[k]; ax[id] = a.x; ay[id] = a.y; az[id] = a.z; }
+}
+
+// Simulation.update's output array (simulation.py:300-304): [N][3] in particle order
+__global__ void __launch_bounds__(kEwThreads)
+k_snapshot(const float4* __restrict__ posw, const float4* __restrict__ veli, int n,
+           float* __restrict__ xyz)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 p = posw[k];
+    const int id = __float_as_int(veli[k].w);
+    xyz[3 * (size_t)id + 0] = p.x;
+    xyz[3 * (size_t)id + 1] = p.y;
+    xyz[3 * (size_t)id + 2] = p.z;
+}
+
+// bins of the last step in the reference's layout
+__global__ void __launch_bounds__(kEwThreads)
+k_export_bins(const float4* __restrict__ veli_sorted, const int* __restrict__ cell_sorted, int n,
+              int* __restrict__ particle_bins, int* __restrict__ particle_indices)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int id = __float_as_int(veli_sorted[k].w);
+    if (particle_bins) particle_bins[id] = cell_sorted[k];
+    if (particle_indices) particle_indices[k] = id;
+}
+
+// reference-layout inputs -> cell-sorted float4 scratch for gof_accelerator
+__global__ void __launch_bounds__(kEwThreads)
+k_gather_sorted(const float* __restrict__ px, const float* __restrict__ py,
+                const float* __restrict__ pz, const float* __restrict__ vx,
+                const float* __restrict__ vy, const float* __restrict__ vz,
+                const int* __restrict__ types, const int* __restrict__ particle_bins,
+                const int* __restrict__ particle_indices, int n, float4* __restrict__ posw,
+                float4* __restrict__ veli, int* __restrict__ cell_sorted)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int id = particle_indices[k];
+    posw[k] = make_float4(px[id], py[id], pz[id], __int_as_float(types[id]));
+    veli[k] = make_float4(vx[id], vy[id], vz[id], __int_as_float(id));
+    cell_sorted[k] = particle_bins[id];
+}
+
+// The timestep of the step being enqueued (integrator.py:174-188) and the reset of the
+// accumulator the force kernel's epilogue will fill for the next one.
+__global__ void k_prepare_dt(StepScalars* s, int parity, float fixed_dt)
+{
+    float dt = fixed_dt;
+    if (fixed_dt < 0.0f) {
+        const double m = sqrt((double)__uint_as_float(s->max_sq_speed_bits[parity]));
+        dt = (m > 1e-6) ? (float)(0.4 / m) : 0.1f;
+    }
+    s->dt = dt;
+    s->max_sq_speed_bits[parity ^ 1] = 0u;
+}
+
+__global__ void k_bits_to_float(const unsigned* bits, float* out) { *out = __uint_as_float(*bits); }
+
+}  // namespace gof
+
+// --------------------------------------------------------------------------------------
+// reference-layout entry points
+// --------------------------------------------------------------------------------------
+extern "C" size_t gof_workspace_bytes(int n, int num_bins, int num_types)
+{
+    if (n < 0) n = 0;
+    size_t b = 0;
+    b += 2 * align_up((size_t)n * sizeof(float4));        // posw, veli (accelerator)
+    b += 3 * align_up((size_t)n * sizeof(int));           // slot ids / cell_sorted / spare
+    b += align_up((size_t)(cdiv(num_bins > 0 ? num_bins : 1, kScanTile) + 1) * sizeof(int));
+    b += species_bytes(num_types > 0 ? num_types : 1);
+    b += 256;
+    return b;
+}
+
+extern "C" int gof_setup_bins(const float* d_pos_x, const float* d_pos_y, const float* d_pos_z,
+                              int n, const gof_grid* grid, int num_bins, int32_t* d_particle_bins,
+                              int32_t* d_counts, int32_t* d_bin_offsets, int32_t* d_starts,
+                              int32_t* d_particle_indices, void* d_workspace, size_t workspace_bytes,
+                              void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    Geometry g;
+    if (int rc = make_geometry(grid, 0, 0, &g)) return rc;
+    if (n < 0 || num_bins < g.num_cells) return fail(GOF_E_INVALID, "gof_setup_bins: num_bins < num_cells");
+    if (!d_pos_x || !d_pos_y || !d_pos_z || !d_particle_bins || !d_counts || !d_bin_offsets || !d_starts ||
+        !d_particle_indices || !d_workspace)
+        return fail(GOF_E_INVALID, "gof_setup_bins: null pointer");
+    if (workspace_bytes < gof_workspace_bytes(n, num_bins, 1)) return fail(GOF_E_NOMEM, "gof_setup_bins: workspace too small");
+    char* w = (char*)d_workspace;
+    int* slot_id = (int*)w;
+    w += align_up((size_t)n * sizeof(int));
+    int* tile_sums = (int*)w;
+
+    GOF_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)num_bins * sizeof(int), st));
+    if (n > 0) {
+        MigrateOut none{};
+        GOF_LAUNCH(k_hash_count<true>, cdiv(n, kBinThreads), kBinThreads, 0, st, (const float4*)nullptr,
+                   (const float4*)nullptr, (const float4*)nullptr, d_pos_x, d_pos_y, d_pos_z, n, g,
+                   d_particle_bins, d_bin_offsets, d_counts, none);
+    }
+    if (int rc = launch_scan(d_counts, num_bins, tile_sums, d_starts, st)) return rc;
+    if (n > 0) {
+        GOF_LAUNCH(k_scatter_ids<true>, cdiv(n, kBinThreads), kBinThreads, 0, st, (const float4*)nullptr, n,
+                   d_particle_bins, d_bin_offsets, d_starts, slot_id, d_particle_indices /* scratch: rewritten below */);
+        GOF_LAUNCH(k_rank_indices, cdiv(n, kBinThreads), kBinThreads, 0, st, n, d_particle_bins, d_starts,
+                   d_counts, slot_id, d_bin_offsets, d_particle_indices);
+    }
+    return 0;
+}
+
+extern "C" int gof_accelerator(const float* d_pos_x, const float* d_pos_y, const float* d_pos_z,
+                               const float* d_vel_x, const float* d_vel_y, const float* d_vel_z, int n,
+                               const gof_grid* grid, const double* pm_host, int num_types,
+                               const int32_t* d_types, float* d_acc_x, float* d_acc_y, float* d_acc_z,
+                               float* d_boid_acc_x, float* d_boid_acc_y, float* d_boid_acc_z,
+                               float* d_boid_vel_x, float* d_boid_vel_y, float* d_boid_vel_z,
+                               int32_t* d_boid_counts, const int32_t* d_particle_bins,
+                               const int32_t* d_particle_indices, const int32_t* d_bin_starts,
+                               const int32_t* d_bin_counts, int wrap_mode, void* d_workspace,
+                               size_t workspace_bytes, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    Geometry g;
+    if (int rc = make_geometry(grid, 0, 0, &g)) return rc;
+    HostSpecies hs;
+    if (int rc = build_species(pm_host, num_types, &hs)) return rc;
+    if (!d_pos_x || !d_pos_y || !d_pos_z || !d_vel_x || !d_vel_y || !d_vel_z || !d_types || !d_acc_x ||
+        !d_acc_y || !d_acc_z || !d_particle_bins || !d_particle_indices || !d_bin_starts || !d_bin_counts ||
+        !d_workspace)
+        return fail(GOF_E_INVALID, "gof_accelerator: null pointer");
+    const bool boid_out = d_boid_counts != nullptr;
+    if (boid_out && (!d_boid_acc_x || !d_boid_acc_y || !d_boid_acc_z || !d_boid_vel_x || !d_boid_vel_y || !d_boid_vel_z))
+        return fail(GOF_E_INVALID, "gof_accelerator: boid outputs must be given together");
+    if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
+        return fail(GOF_E_INVALID, "gof_accelerator: bad wrap_mode");
+    if (workspace_bytes < gof_workspace_bytes(n, g.num_cells, num_types))
+        return fail(GOF_E_NOMEM, "gof_accelerator: workspace too small");
+    if (n <= 0) return 0;
+
+    char* w = (char*)d_workspace;
+    float4* posw = (float4*)w;
+    w += align_up((size_t)n * sizeof(float4));
+    float4* veli = (float4*)w;
+    w += align_up((size_t)n * sizeof(float4));
+    int* cell_sorted = (int*)w;
+    w += 3 * align_up((size_t)n * sizeof(int));
+    w += align_up((size_t)(cdiv(g.num_cells, kScanTile) + 1) * sizeof(int));
+    DeviceSpecies ds = carve_species(w, num_types);
+    if (int rc = upload_species(hs, ds, st)) return rc;
+
+    if (boid_out) {
+        const size_t nt = (size_t)n * num_types;
+        GOF_CUDA(cudaMemsetAsync(d_boid_counts, 0, nt * sizeof(int), st));
+        float* fs[6] = {d_boid_acc_x, d_boid_acc_y, d_boid_acc_z, d_boid_vel_x, d_boid_vel_y, d_boid_vel_z};
+        for (float* f : fs) GOF_CUDA(cudaMemsetAsync(f, 0, nt * sizeof(float), st));
+    }
+    GOF_LAUNCH(k_gather_sorted, cdiv(n, kEwThreads), kEwThreads, 0, st, d_pos_x, d_pos_y, d_pos_z, d_vel_x,
+               d_vel_y, d_vel_z, d_types, d_particle_bins, d_particle_indices, n, posw, veli, cell_sorted);
+    ForceArgs a{};
+    a.posw = posw;
+    a.veli = veli;
+    a.cell_sorted = cell_sorted;
+    a.start = d_bin_starts;
+    a.count = d_bin_counts;
+    a.home_begin = 0;
+    a.home_count = n;
+    a.table = ds.table;
+    a.kind_rows = ds.kind_rows;
+    a.sep_exact = ds.sep_exact;
+    a.self_kind = ds.self_kind;
+    a.T = num_types;
+    a.wrap_mode = wrap_mode;
+    a.acc_x = d_acc_x;
+    a.acc_y = d_acc_y;
+    a.acc_z = d_acc_z;
+    a.boid_counts = d_boid_counts;
+    a.boid_acc_x = d_boid_acc_x;
+    a.boid_acc_y = d_boid_acc_y;
+    a.boid_acc_z = d_boid_acc_z;
+    a.boid_vel_x = d_boid_vel_x;
+    a.boid_vel_y = d_boid_vel_y;
+    a.boid_vel_z = d_boid_vel_z;
+    a.n_total = n;
+    return launch_force(g, a, hs.has_boids, kModeScatter, st);
+}
+
+extern "C" int gof_step1(float* vx, float* vy, float* vz, const float* ax, const float* ay, const float* az,
+                         int n, float timestep, void* stream)
+{
+    if (n <= 0) return 0;
+    if (!vx || !vy || !vz || !ax || !ay || !az) return fail(GOF_E_INVALID, "gof_step1: null pointer");
+    GOF_LAUNCH(k_step1, cdiv(n, kEwThreads), kEwThreads, 0, (cudaStream_t)stream, vx, vy, vz, ax, ay, az, n, timestep);
+    return 0;
+}
+
+extern "C" int gof_step2(float* px, float* py, float* pz, float* vx, float* vy, float* vz, const float* ax,
+                         const float* ay, const float* az, const int32_t* tia, const int32_t* self_kind, int n,
+                         float timestep, void* stream)
+{
+    if (n <= 0) return 0;
+    if (!px || !py || !pz || !vx || !vy || !vz || !ax || !ay || !az || !tia || !self_kind)
+        return fail(GOF_E_INVALID, "gof_step2: null pointer");
+    GOF_LAUNCH(k_step2, cdiv(n, kEwThreads), kEwThreads, 0, (cudaStream_t)stream, px, py, pz, vx, vy, vz, ax, ay,
+               az, tia, self_kind, n, timestep);
+    return 0;
+}
+
+extern "C" int gof_boundary_condition(float* px, float* py, float* pz, float lx, float ly, float lz, int n,
+                                      void* stream)
+{
+    if (n <= 0) return 0;
+    if (!px || !py || !pz) return fail(GOF_E_INVALID, "gof_boundary_condition: null pointer");
+    GOF_LAUNCH(k_boundary, cdiv(n, kEwThreads), kEwThreads, 0, (cudaStream_t)stream, px, py, pz, lx, ly, lz, n);
+    return 0;
+}
+
+extern "C" int gof_max_sq_speed(const float* vx, const float* vy, const float* vz, int n, float* d_out,
+                                void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_out) return fail(GOF_E_INVALID, "gof_max_sq_speed: null output");
+    GOF_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float), st));
+    if (n <= 0) return 0;
+    if (!vx || !vy || !vz) return fail(GOF_E_INVALID, "gof_max_sq_speed: null pointer");
+    int blocks = cdiv(n, kEwThreads);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    // non-negative floats order like their bit patterns, so the float is reduced in place as a uint
+    GOF_LAUNCH(k_max_sq_speed, blocks, kEwThreads, 0, st, vx, vy, vz, n, reinterpret_cast<unsigned*>(d_out));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// the resident engine
+// --------------------------------------------------------------------------------------
+struct gof_engine {
+    int device = 0;
+    int n = 0;          // live particles
+    int capacity = 0;   // slots in the per-particle arrays
+    int T = 0;
+    gof_grid grid{};
+    Geometry geom{};
+    HostSpecies species;
+    bool species_dirty = true;
+    bool bound = false, uploaded = false, binned = false;
+    int parity = 0;  // which max_sq_speed slot describes the resident velocities
+
+    // carved from the arena
+    size_t arena_bytes = 0;
+    float4 *posw[2] = {nullptr, nullptr}, *veli[2] = {nullptr, nullptr}, *acc = nullptr;
+    int *cell_of = nullptr, *off = nullptr, *slot_id = nullptr, *slot_src = nullptr, *cell_sorted = nullptr;
+    int *count = nullptr, *start = nullptr, *tile_sums = nullptr;
+    StepScalars* scalars = nullptr;
+    DeviceSpecies dspecies{};
+    float* stage[9] = {};  // SoA staging: pos xyz, vel xyz, acc xyz
+    int* stage_types = nullptr;
+    int* stage_bins = nullptr;     // particle_bins / particle_indices export
+    int* stage_indices = nullptr;
+    float* stage_xyz = nullptr;    // snapshot [N][3]
+};
+
+static size_t engine_layout(gof_engine* e, char* base)
+{
+    // base == nullptr: only compute the size
+    size_t o = 0;
+    auto take = [&](size_t bytes) -> char* {
+        char* p = base ? base + o : nullptr;
+        o += align_up(bytes);
+        return p;
+    };
+    const size_t cap = (size_t)e->capacity;
+    const size_t cells = (size_t)e->geom.num_cells + 2;
+    for (int b = 0; b < 2; ++b) {
+        e->posw[b] = (float4*)take(cap * sizeof(float4));
+        e->veli[b] = (float4*)take(cap * sizeof(float4));
+    }
+    e->acc = (float4*)take(cap * sizeof(float4));
+    e->cell_of = (int*)take(cap * sizeof(int));
+    e->off = (int*)take(cap * sizeof(int));
+    e->slot_id = (int*)take(cap * sizeof(int));
+    e->slot_src = (int*)take(cap * sizeof(int));
+    e->cell_sorted = (int*)take(cap * sizeof(int));
+    e->count = (int*)take(cells * sizeof(int));
+    e->start = (int*)take(cells * sizeof(int));
+    e->tile_sums = (int*)take((size_t)(cdiv((int)cells, kScanTile) + 1) * sizeof(int));
+    e->scalars = (StepScalars*)take(sizeof(StepScalars));
+    char* sp = take(species_bytes(e->T));
+    if (base) e->dspecies = carve_species(sp, e->T);
+    for (int k = 0; k < 9; ++k) e->stage[k] = (float*)take(cap * sizeof(float));
+    e->stage_types = (int*)take(cap * sizeof(int));
+    e->stage_bins = (int*)take(cap * sizeof(int));
+    e->stage_indices = (int*)take(cap * sizeof(int));
+    e->stage_xyz = (float*)take(cap * 3 * sizeof(float));
+    return o;
+}
+
+extern "C" int gof_engine_create(gof_engine** out, int device, int num_particles, int num_types,
+                                 const gof_grid* grid, const double* pm_host)
+{
+    if (!out || num_particles < 1 || !grid) return fail(GOF_E_INVALID, "gof_engine_create: bad arguments");
+    gof_engine* e = new (std::nothrow) gof_engine();
+    if (!e) return fail(GOF_E_NOMEM, "gof_engine_create: host allocation failed");
+    e->device = device;
+    e->n = e->capacity = num_particles;
+    e->T = num_types;
+    e->grid = *grid;
+    int rc = make_geometry(grid, 0, 0, &e->geom);
+    if (!rc) rc = build_species(pm_host, num_types, &e->species);
+    if (rc) {
+        delete e;
+        return rc;
+    }
+    e->arena_bytes = engine_layout(e, nullptr);
+    *out = e;
+    return 0;
+}
+
+extern "C" void gof_engine_destroy(gof_engine* e) { delete e; }
+
+extern "C" size_t gof_engine_arena_bytes(const gof_engine* e) { return e ? e->arena_bytes : 0; }
+
+extern "C" int gof_engine_bind_arena(gof_engine* e, void* d_arena, size_t bytes)
+{
+    if (!e || !d_arena) return fail(GOF_E_INVALID, "gof_engine_bind_arena: null pointer");
+    if (bytes < e->arena_bytes) return fail(GOF_E_NOMEM, "gof_engine_bind_arena: arena too small");
+    if ((uintptr_t)d_arena % 256) return fail(GOF_E_INVALID, "gof_engine_bind_arena: arena must be 256-byte aligned");
+    GOF_CUDA(cudaSetDevice(e->device));
+    engine_layout(e, (char*)d_arena);
+    e->bound = true;
+    e->uploaded = e->binned = false;
+    e->species_dirty = true;
+    return 0;
+}
+
+extern "C" int gof_engine_set_parameters(gof_engine* e, const double* pm_host, void* stream)
+{
+    if (!e) return fail(GOF_E_INVALID, "null engine");
+    if (int rc = build_species(pm_host, e->T, &e->species)) return rc;
+    e->species_dirty = true;
+    if (e->bound) {
+        GOF_CUDA(cudaSetDevice(e->device));
+        if (int rc = upload_species(e->species, e->dspecies, (cudaStream_t)stream)) return rc;
+        e->species_dirty = false;
+    }
+    return 0;
+}
+
+static int engine_ready(gof_engine* e, bool need_state)
+{
+    if (!e) return fail(GOF_E_INVALID, "null engine");
+    if (!e->bound) return fail(GOF_E_STATE, "engine has no arena: call gof_engine_bind_arena first");
+    if (need_state && !e->uploaded) return fail(GOF_E_STATE, "engine has no state: call gof_engine_upload first");
+    GOF_CUDA(cudaSetDevice(e->device));
+    return 0;
+}
+
+extern "C" int gof_engine_upload(gof_engine* e, const float* px, const float* py, const float* pz,
+                                 const float* vx, const float* vy, const float* vz, const float* ax,
+                                 const float* ay, const float* az, const int32_t* types, void* stream)
+{
+    if (int rc = engine_ready(e, false)) return rc;
+    if (!px || !py || !pz || !types) return fail(GOF_E_INVALID, "gof_engine_upload: positions and types are required");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = e->capacity;
+    const float* src[9] = {px, py, pz, vx, vy, vz, ax, ay, az};
+    for (int k = 0; k < 9; ++k)
+        if (src[k]) GOF_CUDA(cudaMemcpyAsync(e->stage[k], src[k], (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    GOF_CUDA(cudaMemcpyAsync(e->stage_types, types, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
+    if (e->species_dirty) {
+        if (int rc = upload_species(e->species, e->dspecies, st)) return rc;
+        e->species_dirty = false;
+    }
+    GOF_CUDA(cudaMemsetAsync(e->scalars, 0, sizeof(StepScalars), st));
+    e->parity = 0;
+    e->n = n;
+    GOF_LAUNCH(k_pack, cdiv(n, kEwThreads), kEwThreads, 0, st, e->stage[0], e->stage[1], e->stage[2],
+               vx ? e->stage[3] : nullptr, vy ? e->stage[4] : nullptr, vz ? e->stage[5] : nullptr,
+               ax ? e->stage[6] : nullptr, ay ? e->stage[7] : nullptr, az ? e->stage[8] : nullptr,
+               e->stage_types, n, e->posw[0], e->veli[0], e->acc, &e->scalars->max_sq_speed_bits[0]);
+    e->uploaded = true;
+    e->binned = false;
+    return 0;
+}
+
+// setup_bins on the resident state: posw[0]/veli[0]/acc (rest order) -> posw[1]/veli[1]
+// (cell order, velocities kicked by step1 when `kick`), cell tables filled.
+static int engine_bin(gof_engine* e, bool kick, cudaStream_t st)
+{
+    const Geometry& g = e->geom;
+    const int n = e->n;
+    GOF_CUDA(cudaMemsetAsync(e->count, 0, (size_t)(g.num_cells + 2) * sizeof(int), st));
+    MigrateOut none{};
+    GOF_LAUNCH(k_hash_count<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->posw[0], e->veli[0], e->acc,
+               (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, n, g, e->cell_of, e->off,
+               e->count, none);
+    if (int rc = launch_scan(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
+    GOF_LAUNCH(k_scatter_ids<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->veli[0], n, e->cell_of, e->off,
+               e->start, e->slot_id, e->slot_src);
+    GOF_LAUNCH(k_rank_gather_kick, cdiv(n, kBinThreads), kBinThreads, 0, st, n, e->cell_of, e->start, e->count,
+               e->slot_id, e->slot_src, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1],
+               e->cell_sorted, e->scalars, kick ? 1 : 0);
+    e->binned = true;
+    return 0;
+}
+
+static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
+{
+    *a = ForceArgs{};
+    a->posw = e->posw[1];
+    a->veli = e->veli[1];
+    a->cell_sorted = e->cell_sorted;
+    a->start = e->start;
+    a->count = e->count;
+    a->home_begin = 0;
+    a->home_count = e->n;
+    a->table = e->dspecies.table;
+    a->kind_rows = e->dspecies.kind_rows;
+    a->sep_exact = e->dspecies.sep_exact;
+    a->self_kind = e->dspecies.self_kind;
+    a->T = e->T;
+    a->wrap_mode = wrap_mode;
+    a->posw_out = e->posw[0];
+    a->veli_out = e->veli[0];
+    a->acc_out = e->acc;
+    a->scalars = e->scalars;
+    a->n_total = e->n;
+}
+
+extern "C" int gof_engine_step(gof_engine* e, int n_steps, float timestep, int wrap_mode, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
+        return fail(GOF_E_INVALID, "gof_engine_step: bad wrap_mode");
+    if (timestep == 0.0f || timestep != timestep) return fail(GOF_E_INVALID, "gof_engine_step: bad timestep");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s = 0; s < n_steps; ++s) {
+        GOF_LAUNCH(k_prepare_dt, 1, 1, 0, st, e->scalars, e->parity, timestep < 0 ? -1.0f : timestep);
+        if (int rc = engine_bin(e, true, st)) return rc;
+        ForceArgs a;
+        engine_force_args(e, wrap_mode, &a);
+        a.integrate = 1;
+        a.parity_out = e->parity ^ 1;
+        if (int rc = launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st)) return rc;
+        e->parity ^= 1;
+    }
+    return 0;
+}
+
+extern "C" int gof_engine_accelerate(gof_engine* e, int wrap_mode, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
+        return fail(GOF_E_INVALID, "gof_engine_accelerate: bad wrap_mode");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = engine_bin(e, false, st)) return rc;
+    ForceArgs a;
+    engine_force_args(e, wrap_mode, &a);
+    a.integrate = 0;
+    a.parity_out = e->parity;  // velocities unchanged: the maximum is re-accumulated into the same slot
+    return launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st);
+}
+
+extern "C" int gof_engine_download(gof_engine* e, float* px, float* py, float* pz, float* vx, float* vy,
+                                   float* vz, float* ax, float* ay, float* az, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = e->n;
+    const bool wp = px || py || pz, wv = vx || vy || vz, wa = ax || ay || az;
+    GOF_LAUNCH(k_unpack, cdiv(n, kEwThreads), kEwThreads, 0, st, e->posw[0], e->veli[0], e->acc, n,
+               wp ? e->stage[0] : nullptr, e->stage[1], e->stage[2], wv ? e->stage[3] : nullptr, e->stage[4],
+               e->stage[5], wa ? e->stage[6] : nullptr, e->stage[7], e->stage[8]);
+    float* dst[9] = {px, py, pz, vx, vy, vz, ax, ay, az};
+    for (int k = 0; k < 9; ++k)
+        if (dst[k]) GOF_CUDA(cudaMemcpyAsync(dst[k], e->stage[k], (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    return 0;
+}
+
+extern "C" int gof_engine_snapshot(gof_engine* e, float* xyz, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    if (!xyz) return fail(GOF_E_INVALID, "gof_engine_snapshot: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = e->n;
+    GOF_LAUNCH(k_snapshot, cdiv(n, kEwThreads), kEwThreads, 0, st, e->posw[0], e->veli[0], n, e->stage_xyz);
+    GOF_CUDA(cudaMemcpyAsync(xyz, e->stage_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyDefault, st));
+    return 0;
+}
+
+extern "C" int gof_engine_read_bins(gof_engine* e, int32_t* particle_bins, int32_t* bin_counts,
+                                    int32_t* bin_starts, int32_t* particle_indices, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    if (!e->binned) return fail(GOF_E_STATE, "gof_engine_read_bins: no step or accelerate has run since the upload");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = e->n;
+    // posw[1]/veli[1] still hold the cell-ordered snapshot the last force kernel read
+    GOF_LAUNCH(k_export_bins, cdiv(n, kEwThreads), kEwThreads, 0, st, e->veli[1], e->cell_sorted, n,
+               e->stage_bins, e->stage_indices);
+    if (particle_bins) GOF_CUDA(cudaMemcpyAsync(particle_bins, e->stage_bins, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
+    if (particle_indices) GOF_CUDA(cudaMemcpyAsync(particle_indices, e->stage_indices, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
+    const size_t cb = (size_t)e->geom.num_cells * sizeof(int);
+    if (bin_counts) GOF_CUDA(cudaMemcpyAsync(bin_counts, e->count, cb, cudaMemcpyDefault, st));
+    if (bin_starts) GOF_CUDA(cudaMemcpyAsync(bin_starts, e->start, cb, cudaMemcpyDefault, st));
+    return 0;
+}
+
+extern "C" int gof_engine_last_timestep(gof_engine* e, float* out, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    if (!out) return fail(GOF_E_INVALID, "gof_engine_last_timestep: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    GOF_CUDA(cudaMemcpyAsync(out, &e->scalars->dt, sizeof(float), cudaMemcpyDeviceToHost, st));
+    GOF_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -1,0 +1,282 @@
+// gof_binning.cuh -- cell hash, warp-aggregated counts, exclusive scan and the
+// stable counting-sort scatter that reorders particles by cell.
+//
+// Replaces the reference's bin_particles / cumsum / set_indices
+// (main/acceleration_updater.py:38-135).  The reference never moves particle
+// data: it keeps an index permutation.  Here the permutation is applied to the
+// float4 state every step so that the force kernel streams contiguous cells.
+//
+// Order inside a cell: by particle id (the reference's particle index).  That
+// is what the reference's atomic hands out when threads arrive in index order
+// and what its serial restatement (oracle/gof_oracle.c) produces, so
+// particle_indices is bit-exact and deterministic.  The GPU gets there in two
+// moves: an atomic (arrival-order) scatter of ids into the cell's segment, then
+// a rank pass that counts, for every slot, the smaller ids in its segment.
+#pragma once
+#include "gof_kernels.cuh"
+
+namespace gof {
+
+constexpr int kBinThreads = 256;
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// Slab-mode send buffers for particles that left the owned layers (START-of-step
+// migration; see slab.py).  All pointers may be null on a single GPU.
+struct MigrateOut {
+    float4* down_posw; float4* down_veli; float4* down_acc;
+    float4* up_posw;   float4* up_veli;   float4* up_acc;
+    int* counters;   // [0] = number going down, [1] = going up, [2] = error flag
+    int capacity;
+};
+
+// Cell of every particle + per-cell population.  One atomic per distinct cell per
+// warp (__match_any_sync groups lanes that hit the same cell; after the first
+// step the arrays are already almost sorted, so a warp touches one or two cells).
+//   SOA = true : reference-layout inputs x[], y[], z[] in particle order (gof_setup_bins)
+//   SOA = false: the engine's float4 {x, y, z, type}; type < 0 marks a dead slot.
+// `off` receives the arrival-order offset inside the cell (the reference's
+// bin_offsets before it is made deterministic by the rank pass).
+template <bool SOA>
+__global__ void __launch_bounds__(kBinThreads)
+k_hash_count(const float4* __restrict__ posw, const float4* __restrict__ veli,
+             const float4* __restrict__ acc, const float* __restrict__ px,
+             const float* __restrict__ py, const float* __restrict__ pz, int n,
+             const __grid_constant__ Geometry g, int* __restrict__ cell_of,
+             int* __restrict__ off, int* __restrict__ count, MigrateOut mig)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cell = -1;
+    if (i < n) {
+        float x, y, z;
+        bool dead = false;
+        if (SOA) {
+            x = px[i]; y = py[i]; z = pz[i];
+        } else {
+            const float4 p = posw[i];
+            x = p.x; y = p.y; z = p.z;
+            dead = __float_as_int(p.w) < 0;
+        }
+        if (dead) {
+            cell = g.num_cells;  // sentinel bin: sorts behind every live particle
+        } else {
+            const int cx = bin_coord(x, g.bsx, g.nbx);
+            const int cy = bin_coord(y, g.bsy, g.nby);
+            int lz = 0;
+            if (g.is3d) {
+                const int cz = bin_coord(z, g.bsz, g.nbz);
+                lz = cz - g.layer_base;
+                if (!g.index_wrap_z) {  // slab: local layer of a global layer, periodic
+                    if (lz >= g.nbz) lz -= g.nbz;
+                    if (lz < 0) lz += g.nbz;
+                }
+            }
+            cell = cx + g.nbx * (cy + g.nby * lz);
+            if (!SOA && !g.index_wrap_z && g.is3d) {
+                // slab mode: a particle in a halo layer has left; hand it to the neighbour
+                const bool down = (lz == 0), up = (lz == g.nlz - 1);
+                if (down || up || lz >= g.nlz) {
+                    if (lz >= g.nlz || mig.counters == nullptr) {
+                        if (mig.counters) atomicExch(&mig.counters[2], 1);
+                    } else {
+                        const int k = atomicAdd(&mig.counters[down ? 0 : 1], 1);
+                        if (k < mig.capacity) {
+                            (down ? mig.down_posw : mig.up_posw)[k] = posw[i];
+                            (down ? mig.down_veli : mig.up_veli)[k] = veli[i];
+                            (down ? mig.down_acc : mig.up_acc)[k] = acc[i];
+                        } else {
+                            atomicExch(&mig.counters[2], 2);
+                        }
+                    }
+                    cell = g.num_cells;
+                }
+            }
+        }
+        cell_of[i] = cell;
+    }
+    // warp-aggregated atomic: lanes with the same cell elect a leader
+    const unsigned active = __ballot_sync(0xffffffffu, cell >= 0);
+    if (cell >= 0) {
+        const unsigned peers = __match_any_sync(active, cell);
+        const int leader = __ffs(peers) - 1;
+        const int rank = __popc(peers & ((1u << lane_id()) - 1u));
+        int base = 0;
+        if (lane_id() == leader) base = atomicAdd(&count[cell], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        off[i] = base + rank;
+    }
+}
+
+// ---- exclusive scan of the cell counts (block-level scans, reduce-then-scan) ----
+
+__device__ __forceinline__ int warp_inclusive_scan(int v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= d) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan of one int per thread (kScanThreads threads); returns the
+// exclusive prefix and, through `total`, the block sum.
+__device__ __forceinline__ int block_exclusive_scan(int v, int& total)
+{
+    __shared__ int warp_sums[32];
+    const int inc = warp_inclusive_scan(v);
+    const int w = threadIdx.x >> 5;
+    if (lane_id() == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        int s = lane_id() < nw ? warp_sums[lane_id()] : 0;
+        s = warp_inclusive_scan(s);
+        warp_sums[lane_id()] = s;
+    }
+    __syncthreads();
+    const int warp_prefix = w ? warp_sums[w - 1] : 0;
+    total = warp_sums[31];
+    __syncthreads();
+    return warp_prefix + inc - v;
+}
+
+// Phase 1: sum of every tile of kScanTile counts.
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_tile_sums(const int* __restrict__ in, int m, int* __restrict__ tile_sums)
+{
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < m) s += in[base + k];
+    int total;
+    block_exclusive_scan(s, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// Phase 2: one block turns the tile sums into exclusive tile prefixes (loops if needed).
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_tile_prefix(int* __restrict__ tile_sums, int tiles)
+{
+    int carry = 0;
+    for (int base = 0; base < tiles; base += kScanThreads) {
+        const int idx = base + threadIdx.x;
+        const int v = idx < tiles ? tile_sums[idx] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, total);
+        if (idx < tiles) tile_sums[idx] = carry + ex;
+        carry += total;
+    }
+}
+
+// Phase 3: scan inside each tile and add the tile prefix.  With a single tile
+// (up to 4096 cells: every configuration the reference UI can build) phases 1
+// and 2 are skipped and this is the whole scan.
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_prefix,
+             int* __restrict__ out)
+{
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < m) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int ex = block_exclusive_scan(s, total) + (tile_prefix ? tile_prefix[blockIdx.x] : 0);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < m) out[base + k] = ex;
+        ex += v[k];
+    }
+}
+
+// Arrival-order scatter of (id, source index) into the cell segments.
+template <bool SOA>
+__global__ void __launch_bounds__(kBinThreads)
+k_scatter_ids(const float4* __restrict__ veli, int n, const int* __restrict__ cell_of,
+              const int* __restrict__ off, const int* __restrict__ start,
+              int* __restrict__ slot_id, int* __restrict__ slot_src)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = start[cell_of[i]] + off[i];
+    slot_id[s] = SOA ? i : __float_as_int(veli[i].w);
+    slot_src[s] = i;
+}
+
+// Rank pass for the reference-layout API: final position of every particle in its
+// cell = number of smaller ids in the segment.  Writes the reference's outputs.
+__global__ void __launch_bounds__(kBinThreads)
+k_rank_indices(int n, const int* __restrict__ cell_of, const int* __restrict__ start,
+               const int* __restrict__ count, const int* __restrict__ slot_id,
+               int* __restrict__ bin_offsets, int* __restrict__ particle_indices)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int id = slot_id[s];
+    const int c = cell_of[id];
+    const int b = start[c], e = b + count[c];
+    int rank = 0;
+    for (int t = b; t < e; ++t) rank += (slot_id[t] < id);
+    bin_offsets[id] = rank;
+    particle_indices[b + rank] = id;
+}
+
+// Rank pass of the engine, fused with the gather that physically reorders the
+// state and with integrator.step1 (main/integrator.py:33-55: half kick with the
+// previous acceleration, then the speed clamp).  step1 has to be finished for
+// every particle before the force kernel runs because Boids alignment reads
+// the neighbours' kicked velocities, and this pass rewrites the velocities anyway.
+//   in : posw/veli/acc in last step's order (+ appended arrivals)
+//   out: posw/veli in this step's cell order, cell_sorted
+// `dt_in` < 0: read the adaptive timestep from scalars (see k_prepare_dt).
+struct StepScalars {
+    unsigned max_sq_speed_bits[2];  // ping-pong: fp32 bit pattern of max |v|^2 (non-negative => uint order)
+    float dt;                       // timestep of the step being enqueued
+    int error;                      // sticky device-side error flags
+};
+
+__global__ void __launch_bounds__(kBinThreads)
+k_rank_gather_kick(int n, const int* __restrict__ cell_of, const int* __restrict__ start,
+                   const int* __restrict__ count, const int* __restrict__ slot_id,
+                   const int* __restrict__ slot_src, int sentinel_cell,
+                   const float4* __restrict__ posw_in, const float4* __restrict__ veli_in,
+                   const float4* __restrict__ acc_in, float4* __restrict__ posw_out,
+                   float4* __restrict__ veli_out, int* __restrict__ cell_sorted,
+                   const StepScalars* __restrict__ scalars, int apply_kick)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int src = slot_src[s];
+    const int c = cell_of[src];
+    if (c == sentinel_cell) return;  // dead slot: dropped by the sort
+    const int id = slot_id[s];
+    const int b = start[c], e = b + count[c];
+    int rank = 0;
+    for (int t = b; t < e; ++t) rank += (slot_id[t] < id);
+    const int dst = b + rank;
+
+    float4 v = veli_in[src];
+    if (apply_kick) {
+        const float4 a = acc_in[src];
+        const float h = 0.5f * scalars->dt;
+        v.x = fmaf(a.x, h, v.x);
+        v.y = fmaf(a.y, h, v.y);
+        v.z = fmaf(a.z, h, v.z);
+        const float sq = v.x * v.x + v.y * v.y + v.z * v.z;
+        if (sq > kMaxSpeed * kMaxSpeed) {
+            const float k = kMaxSpeed / sqrtf(sq);
+            v.x *= k; v.y *= k; v.z *= k;
+        }
+    }
+    posw_out[dst] = posw_in[src];
+    veli_out[dst] = v;
+    cell_sorted[dst] = c;
+}
+
+}  // namespace gof

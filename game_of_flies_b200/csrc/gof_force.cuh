@@ -1,0 +1,373 @@
+// gof_force.cuh -- the neighbour force kernel with the integrator fused into its
+// epilogue.
+//
+// Replaces the reference's accelerator kernel (main/acceleration_updater.py:219-458)
+// and, in INTEGRATE mode, step2 + boundary_condition + set_sq_speed/max_reduction
+// (main/integrator.py:58-129).
+//
+// The reference walks HALF the stencil (5 / 14 bins) and pushes the reaction
+// onto the neighbour with atomics.  Here every particle GATHERS over the full
+// 9 / 27 cell stencil: no atomics on the accelerations, a fixed summation
+// order (rows in (dz, dy) order, cells by x, particles by id) and therefore
+// bit-reproducible results.  Because the particles are sorted by cell, the
+// three x-adjacent cells of a stencil row are ONE contiguous run of the float4
+// position array; consecutive threads are consecutive particles of the same
+// cell, so all lanes of a warp read the same neighbour at the same time (one
+// 16-byte broadcast load served by L1).
+#pragma once
+#include "gof_binning.cuh"
+
+namespace gof {
+
+constexpr int kForceThreads = 128;
+constexpr int kBoidSlots = 7;  // per partner type: count, sum of relative positions (3), sum of velocities (3)
+
+enum ForceMode : int {
+    kModeIntegrate = 0,  // engine: fused step2 + boundary condition + max |v|^2, outputs in cell order
+    kModeScatter = 1,    // reference-layout API: accelerations (and boid sums) scattered to particle order
+};
+
+struct ForceArgs {
+    const float4* posw;       // {x, y, z, type bits}, cell order (owned + appended halo)
+    const float4* veli;       // {vx, vy, vz, id bits}, cell order, already kicked by step1
+    const int* cell_sorted;   // cell of every home particle
+    const int* start;         // first index of every cell
+    const int* count;         // population of every cell
+    int home_begin, home_count;
+    const PairParam* table;   // [T*T]
+    const unsigned* kind_rows;  // [T] bit j of row i set => (i, j) is of Boids kind
+    const double* sep_exact;  // [T*T] args[0] / 5 in float64 (guard band of the separation radius)
+    const int* self_kind;     // [T] parameter_matrix[-1, t, t]
+    int T;
+    int wrap_mode;
+    // kModeIntegrate
+    float4* posw_out; float4* veli_out; float4* acc_out;
+    StepScalars* scalars; int parity_out;
+    int integrate;            // 0: leave positions and velocities as they are, only store the acceleration
+    // kModeScatter (indexed by particle id)
+    float* acc_x; float* acc_y; float* acc_z;
+    int* boid_counts; float* boid_acc_x; float* boid_acc_y; float* boid_acc_z;
+    float* boid_vel_x; float* boid_vel_y; float* boid_vel_z;
+    int n_total;
+};
+
+// Per-thread state of the particle being updated.
+struct Home {
+    float x, y, z;          // raw position
+    float vx, vy, vz;       // kicked velocity
+    float ax, ay, az;       // accumulated acceleration
+    int type;
+    unsigned kinds;         // kind_rows[type]
+};
+
+// Exact (float64) re-evaluation of the squared distance, in the operation order of
+// the reference (`pos_2 -= limit` first, then `pos[i] - pos_2`, then dx*dx + dy*dy + dz*dz
+// without contraction).  Only reached inside the guard band around r_max^2.
+__device__ __noinline__ bool exact_in_range(const Geometry& g, float xi, float yi, float zi,
+                                            const float4& pj, int sx, int sy, int sz,
+                                            double* dist2_out)
+{
+    const double x2 = sx ? __dsub_rn((double)pj.x, sx * g.Lxd) : (double)pj.x;
+    const double y2 = sy ? __dsub_rn((double)pj.y, sy * g.Lyd) : (double)pj.y;
+    const double z2 = sz ? __dsub_rn((double)pj.z, sz * g.Lzd) : (double)pj.z;
+    const double dx = __dsub_rn((double)xi, x2), dy = __dsub_rn((double)yi, y2),
+                 dz = __dsub_rn((double)zi, z2);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (dist2_out) *dist2_out = d2;
+    return (1e-10 < d2) && (d2 < g.r2d);
+}
+
+// One accepted pair: add what j does to the home particle.
+//   (dx, dy, dz) = home - neighbour (after the periodic shift), d2 = |d|^2
+//   (rx, ry, rz) = neighbour - home as the reference accumulates it for cohesion
+//   exact_d2()   = the float64 squared distance, evaluated only on the edge of r_sep
+template <bool BOIDS, typename ExactD2>
+__device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ tab, int T,
+                                         float* __restrict__ boid_acc, const ForceArgs& a,
+                                         int j, int tj, float dx, float dy, float dz, float rx,
+                                         float ry, float rz, float d2, ExactD2 exact_d2)
+{
+    const float inv = rsqrtf(d2);
+    const float dist = d2 * inv;
+    const PairParam q = tab[h.type * T + tj];
+    if (!BOIDS || !((h.kinds >> tj) & 1u)) {
+        // clusters(): piecewise linear profile, force along the separation vector
+        const float f_in = fmaf(-q.a.y, dist, q.a.z);
+        const float f_tri = fmaf(-q.b.x, fabsf(dist - q.a.w), q.b.y);
+        const float s = (dist < q.a.x ? f_in : f_tri) * inv;
+        h.ax = fmaf(-s, dx, h.ax);
+        h.ay = fmaf(-s, dy, h.ay);
+        h.az = fmaf(-s, dz, h.az);
+    } else {
+        // boids(): separation inside r_sep, and the per-type sums for cohesion / alignment
+        bool sep = dist < q.a.x;
+        if (fabsf(dist - q.a.x) < 4e-6f * q.a.x) {
+            // on the edge of the separation radius the decision is taken in float64
+            sep = sqrt(exact_d2()) < a.sep_exact[h.type * T + tj];
+        }
+        if (sep) {
+            const float s = q.a.y * inv;
+            h.ax = fmaf(s, dx, h.ax);
+            h.ay = fmaf(s, dy, h.ay);
+            h.az = fmaf(s, dz, h.az);
+        }
+        const float4 vj = ldg4(a.veli + j);
+        float* slot = boid_acc + tj * kBoidSlots * kForceThreads;
+        slot[0 * kForceThreads] += 1.0f;
+        slot[1 * kForceThreads] += rx;
+        slot[2 * kForceThreads] += ry;
+        slot[3 * kForceThreads] += rz;
+        slot[4 * kForceThreads] += vj.x;
+        slot[5 * kForceThreads] += vj.y;
+        slot[6 * kForceThreads] += vj.z;
+    }
+}
+
+// A contiguous run [s, e) of neighbour particles seen with one periodic shift
+// (sx, sy, sz) in {-1, 0, 1}: the home particle is moved by shift * L so that
+// `home - neighbour` is the minimum-image separation.
+template <bool BOIDS>
+__device__ __forceinline__ void run_pairs(Home& h, const PairParam* __restrict__ tab, int T,
+                                          float* __restrict__ boid_acc, const ForceArgs& a,
+                                          const Geometry& g, int s, int e, int sx, int sy, int sz)
+{
+    const float xs = h.x + sx * g.Lx, ys = h.y + sy * g.Ly, zs = h.z + sz * g.Lz;
+#pragma unroll 2
+    for (int j = s; j < e; ++j) {
+        const float4 pj = ldg4(a.posw + j);
+        const float dx = xs - pj.x, dy = ys - pj.y, dz = zs - pj.z;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d2 < g.r2_hi && d2 > 1e-10f) {
+            bool ok = true;
+            if (d2 > g.r2_lo) ok = exact_in_range(g, h.x, h.y, h.z, pj, sx, sy, sz, nullptr);
+            if (ok)
+                interact<BOIDS>(h, tab, T, boid_acc, a, j, __float_as_int(pj.w), dx, dy, dz, -dx,
+                                -dy, -dz, d2, [&]() {
+                                    double d2d;
+                                    exact_in_range(g, h.x, h.y, h.z, pj, sx, sy, sz, &d2d);
+                                    return d2d;
+                                });
+        }
+    }
+}
+
+// The reference's z wrap (acceleration_updater.py:325-328) tests pos_y[i] where it
+// means pos_z[i]; which particle plays "i" depends on which of the two bins lists
+// the other in the HALF stencil.  In GOF_WRAP_REFERENCE mode warps whose home cells
+// touch the bottom or top layer therefore take this literal per-pair path, cell by
+// cell (no x merging), with the comparisons in float64 like the reference.
+//   direct : the home particle is the reference's thread i, the neighbour its j
+//   !direct: the neighbour is thread i and updated the home particle as its j
+template <bool BOIDS>
+__device__ __noinline__ void run_pairs_zquirk(Home& h, const PairParam* __restrict__ tab, int T,
+                                              float* __restrict__ boid_acc, const ForceArgs& a,
+                                              const Geometry& g, int s, int e, int sx, int sy,
+                                              bool direct)
+{
+    const float xs = h.x + sx * g.Lx, ys = h.y + sy * g.Ly;
+    const double R = g.rmaxd, Lz = g.Lzd, top = g.Lzd - g.rmaxd;
+    for (int j = s; j < e; ++j) {
+        const float4 pj = ldg4(a.posw + j);
+        const double zi = h.z, zj = pj.z;
+        double dzd, relz;
+        if (direct) {
+            double z2 = zj;
+            if (zi < R && z2 > top) z2 -= Lz;
+            else if (z2 < R && (double)h.y > top) z2 += Lz;
+            dzd = zi - z2;
+            relz = z2 - zi;
+        } else {
+            double z2 = zi;  // the neighbour (thread i) wraps the home particle (its j)
+            if (zj < R && z2 > top) z2 -= Lz;
+            else if (z2 < R && (double)pj.y > top) z2 += Lz;
+            dzd = z2 - zj;
+            double zw = zj;  // ... and accumulates ITS position min-imaged towards the home particle
+            if (zi < R && zw > top) zw -= Lz;
+            else if (zw < R && zi > top) zw += Lz;
+            relz = zw - zi;
+        }
+        const float dx = xs - pj.x, dy = ys - pj.y, dz = (float)dzd;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d2 < g.r2_hi && d2 > 1e-10f) {
+            auto exact = [&]() {
+                const double x2 = sx ? __dsub_rn((double)pj.x, sx * g.Lxd) : (double)pj.x;
+                const double y2 = sy ? __dsub_rn((double)pj.y, sy * g.Lyd) : (double)pj.y;
+                const double ddx = __dsub_rn((double)h.x, x2), ddy = __dsub_rn((double)h.y, y2);
+                return __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
+                                 __dmul_rn(dzd, dzd));
+            };
+            bool ok = true;
+            if (d2 > g.r2_lo) {
+                const double d2d = exact();
+                ok = (1e-10 < d2d) && (d2d < g.r2d);
+            }
+            if (ok)
+                interact<BOIDS>(h, tab, T, boid_acc, a, j, __float_as_int(pj.w), dx, dy, dz, -dx,
+                                -dy, (float)relz, d2, exact);
+        }
+    }
+}
+
+template <bool BOIDS, int MODE>
+__global__ void __launch_bounds__(kForceThreads)
+k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
+{
+    extern __shared__ float4 smem_raw[];
+    PairParam* tab = reinterpret_cast<PairParam*>(smem_raw);
+    const int T = a.T;
+    float* boid_acc = reinterpret_cast<float*>(tab + T * T) + threadIdx.x;
+    for (int q = threadIdx.x; q < T * T; q += blockDim.x) tab[q] = a.table[q];
+    if (BOIDS) {
+        for (int q = 0; q < T * kBoidSlots; ++q) boid_acc[q * kForceThreads] = 0.0f;
+    }
+    __syncthreads();
+
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = local < a.home_count;
+    const int k = a.home_begin + (valid ? local : a.home_count - 1);
+
+    const float4 pi = a.posw[k];
+    const float4 vi = a.veli[k];
+    Home h;
+    h.x = pi.x; h.y = pi.y; h.z = pi.z;
+    h.vx = vi.x; h.vy = vi.y; h.vz = vi.z;
+    h.ax = h.ay = h.az = 0.0f;
+    h.type = __float_as_int(pi.w);
+    h.kinds = BOIDS ? a.kind_rows[h.type] : 0u;
+
+    const int c = a.cell_sorted[k];
+    const int cx = c % g.nbx;
+    const int cyz = c / g.nbx;
+    const int cy = cyz % g.nby;
+    const int lz = cyz / g.nby;
+    const int gz = lz + g.layer_base;  // global layer
+
+    // does this warp need the literal z-wrap path?
+    const bool edge_layer = g.is3d && a.wrap_mode == kWrapReference &&
+                            (gz == 0 || gz == g.nbz - 1);
+    const bool quirk = __any_sync(0xffffffffu, valid && edge_layer);
+
+    const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
+    if (!quirk) {
+        for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
+            int nl = lz + dzi, sz = 0;
+            if (g.is3d) {
+                const int ngz = gz + dzi;
+                if (ngz < 0) { sz = 1; if (g.index_wrap_z) nl += g.nbz; }
+                else if (ngz >= g.nbz) { sz = -1; if (g.index_wrap_z) nl -= g.nbz; }
+            }
+            for (int dyi = -1; dyi <= 1; ++dyi) {
+                int ny = cy + dyi, sy = 0;
+                if (ny < 0) { ny += g.nby; sy = 1; }
+                else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
+                const int rb = (nl * g.nby + ny) * g.nbx;
+                // the x-adjacent cells that need no shift are one contiguous run
+                const int lo = cx > 0 ? cx - 1 : 0;
+                const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
+                int s = a.start[rb + lo];
+                int e = a.start[rb + hi] + a.count[rb + hi];
+                if (!valid) e = s;
+                run_pairs<BOIDS>(h, tab, T, boid_acc, a, g, s, e, 0, sy, sz);
+                // the cell across the periodic x boundary, if the home cell is on the edge
+                if (cx == 0 || cx == g.nbx - 1) {
+                    const int wc = cx == 0 ? g.nbx - 1 : 0;
+                    s = a.start[rb + wc];
+                    e = valid ? s + a.count[rb + wc] : s;
+                    run_pairs<BOIDS>(h, tab, T, boid_acc, a, g, s, e, cx == 0 ? 1 : -1, sy, sz);
+                }
+            }
+        }
+    } else {
+        for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
+            int nl = lz + dzi;
+            const int ngz = gz + dzi;
+            if (g.index_wrap_z) {
+                if (ngz < 0) nl += g.nbz;
+                else if (ngz >= g.nbz) nl -= g.nbz;
+            }
+            for (int dyi = -1; dyi <= 1; ++dyi) {
+                int ny = cy + dyi, sy = 0;
+                if (ny < 0) { ny += g.nby; sy = 1; }
+                else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
+                const int rb = (nl * g.nby + ny) * g.nbx;
+                for (int dxi = -1; dxi <= 1; ++dxi) {
+                    int nx = cx + dxi, sx = 0;
+                    if (nx < 0) { nx += g.nbx; sx = 1; }
+                    else if (nx >= g.nbx) { nx -= g.nbx; sx = -1; }
+                    // half stencil of set_bin_neighbours (acceleration_updater.py:140-215)
+                    const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
+                    const int s = a.start[rb + nx];
+                    const int e = valid ? s + a.count[rb + nx] : s;
+                    run_pairs_zquirk<BOIDS>(h, tab, T, boid_acc, a, g, s, e, sx, sy, direct);
+                }
+            }
+        }
+    }
+
+    // ---- cohesion and alignment from the per-type means (acceleration_updater.py:422-458) ----
+    const int id = __float_as_int(vi.w);
+    if (BOIDS) {
+        const float spd = sqrtf(h.vx * h.vx + h.vy * h.vy + h.vz * h.vz);
+        for (int t = 0; t < T; ++t) {
+            const float* slot = boid_acc + t * kBoidSlots * kForceThreads;
+            const float cnt = slot[0];
+            if (MODE == kModeScatter && a.boid_counts && valid) {
+                const size_t o = (size_t)t * a.n_total + id;
+                a.boid_counts[o] = (int)cnt;
+                a.boid_acc_x[o] = fmaf(cnt, h.x, slot[1 * kForceThreads]);
+                a.boid_acc_y[o] = fmaf(cnt, h.y, slot[2 * kForceThreads]);
+                a.boid_acc_z[o] = fmaf(cnt, h.z, slot[3 * kForceThreads]);
+                a.boid_vel_x[o] = slot[4 * kForceThreads];
+                a.boid_vel_y[o] = slot[5 * kForceThreads];
+                a.boid_vel_z[o] = slot[6 * kForceThreads];
+            }
+            if (((h.kinds >> t) & 1u) && cnt > 0.0f) {
+                const PairParam q = tab[h.type * T + t];
+                const float ic = 1.0f / cnt;
+                const float mx = slot[4 * kForceThreads] * ic, my = slot[5 * kForceThreads] * ic,
+                            mz = slot[6 * kForceThreads] * ic;
+                const float proj = spd > 10.0f ? (mx * h.vx + my * h.vy + mz * h.vz) / spd : 0.0f;
+                h.ax += q.a.w * (slot[1 * kForceThreads] * ic) + q.a.z * (mx - proj * h.vx);
+                h.ay += q.a.w * (slot[2 * kForceThreads] * ic) + q.a.z * (my - proj * h.vy);
+                h.az += q.a.w * (slot[3 * kForceThreads] * ic) + q.a.z * (mz - proj * h.vz);
+            }
+        }
+    }
+
+    if (MODE == kModeScatter) {
+        if (valid) {
+            a.acc_x[id] = h.ax;
+            a.acc_y[id] = h.ay;
+            a.acc_z[id] = h.az;
+        }
+        return;
+    }
+
+    // ---- integrator.step2 + boundary_condition (main/integrator.py:58-114) ----
+    float x = h.x, y = h.y, z = h.z, vx = h.vx, vy = h.vy, vz = h.vz;
+    if (a.integrate) {
+        const float dt = a.scalars->dt;
+        x += (h.vx + 0.5f * h.ax * dt) * dt;
+        y += (h.vy + 0.5f * h.ay * dt) * dt;
+        z += (h.vz + 0.5f * h.az * dt) * dt;
+        vx = fmaf(h.ax, 0.5f * dt, h.vx);
+        vy = fmaf(h.ay, 0.5f * dt, h.vy);
+        vz = fmaf(h.az, 0.5f * dt, h.vz);
+        if (a.self_kind[h.type] == 0) { vx *= kDamping; vy *= kDamping; vz *= kDamping; }
+        if (x < 0.0f) x += g.Lx; else if (x > g.Lx) x -= g.Lx;
+        if (y < 0.0f) y += g.Ly; else if (y > g.Ly) y -= g.Ly;
+        if (z < 0.0f) z += g.Lz; else if (z > g.Lz) z -= g.Lz;
+    }
+    float sq = 0.0f;
+    if (valid) {
+        a.posw_out[k] = make_float4(x, y, z, pi.w);
+        a.veli_out[k] = make_float4(vx, vy, vz, vi.w);
+        a.acc_out[k] = make_float4(h.ax, h.ay, h.az, 0.0f);
+        sq = vx * vx + vy * vy + vz * vz;
+    }
+    // max |v|^2 for the next step's adaptive timestep (integrator.py:174-188)
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(sq));
+    if (lane_id() == 0) atomicMax(&a.scalars->max_sq_speed_bits[a.parity_out], m);
+}
+
+}  // namespace gof

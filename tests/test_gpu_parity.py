@@ -1,0 +1,329 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the oracle on the same
+fp32 state.  Integer outputs bit-exact; accelerations within 1e-5 relative
+(BASELINE.json north_star); positions/velocities after one step accordingly.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_files
+from oracle import oracle as orc
+from parity_util import acc_errors, f32_state, oracle_sim, random_state
+
+pytestmark = pytest.mark.gpu
+
+ACC_RTOL = 1e-5  # single-step accelerations (north_star)
+
+FILES = golden_files()
+IDS = [os.path.basename(f)[:-4] for f in FILES]
+
+
+@pytest.fixture(scope="module")
+def gof():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import game_of_flies_b200.integrator as integ
+    import game_of_flies_b200.acceleration_updater as au
+    import game_of_flies_b200.device as dev
+    import game_of_flies_b200.engine as eng
+    import game_of_flies_b200._lib as lib
+    class NS: pass
+    ns = NS()
+    ns.torch, ns.integ, ns.au, ns.dev, ns.eng, ns.lib = torch, integ, au, dev, eng, lib
+    return ns
+
+
+def golden_state(path, step):
+    g = np.load(path)
+    st = dict(pos=f32_state(g[f"s{step}_in_pos"]), vel=f32_state(g[f"s{step}_in_vel"]),
+              acc=f32_state(g[f"s{step}_in_acc"]), types=g["particle_type_index_array"].astype(np.int32),
+              parameter_matrix=g["parameter_matrix"], limits=g["limits"], r_max=float(g["r_max"]),
+              n=int(g["num_particles"]), T=int(g["num_types"]))
+    ts = None if np.isnan(g["timestep"]) else float(g["timestep"])
+    return st, ts, int(g["steps"])
+
+
+def run_setup_bins(gof, pos, grid_dict):
+    n = pos.shape[1]
+    d = [gof.dev.to_device(pos[k]) for k in range(3)]
+    i32 = gof.torch.int32
+    pb, off, idx = (gof.dev.device_array(n, i32) for _ in range(3))
+    cnt, st = (gof.dev.device_array(grid_dict["num_bins"], i32) for _ in range(2))
+    gd = grid_dict
+    gof.integ.setup_bins(d[0], d[1], d[2], gd["num_bin_x"], gd["num_bin_y"], gd["num_bin_z"],
+                         gd["bin_size_x"], gd["bin_size_y"], gd["bin_size_z"], gd["num_bins"], n,
+                         pb, cnt, off, st, idx)
+    return d, pb, cnt, off, st, idx
+
+
+def check_bins_against_oracle(gof, st):
+    o = oracle_sim(st)
+    o.setup_bins()
+    d, pb, cnt, off, stt, idx = run_setup_bins(gof, st["pos"], o.grid)
+    assert np.array_equal(pb.copy_to_host(), o.particle_bins)
+    assert np.array_equal(cnt.copy_to_host(), o.particle_bin_counts)
+    assert np.array_equal(stt.copy_to_host(), o.particle_bin_starts)
+    assert np.array_equal(off.copy_to_host(), o.bin_offsets)
+    assert np.array_equal(idx.copy_to_host(), o.particle_indices)
+    return o, (d, pb, cnt, off, stt, idx)
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_setup_bins_bit_exact_on_golden_states(gof, path):
+    st, _, steps = golden_state(path, 0)
+    check_bins_against_oracle(gof, st)
+    st, _, _ = golden_state(path, steps - 1)
+    check_bins_against_oracle(gof, st)
+
+
+@pytest.mark.parametrize("limits,n", [((100, 100, 0), 50_000), ((120, 90, 150), 60_000), ((64, 64, 64), 1)])
+def test_setup_bins_bit_exact_random_and_boundary_positions(gof, limits, n):
+    st = random_state([n], limits, seed=7)
+    grid = orc.grid_from_limits(st["limits"], st["r_max"])
+    # adversarial: coordinates on and next to every bin edge, zero, and just inside the box
+    pos = st["pos"]
+    k = 0
+    for axis, (nb, bs, L) in enumerate(((grid["num_bin_x"], grid["bin_size_x"], limits[0]),
+                                        (grid["num_bin_y"], grid["bin_size_y"], limits[1]),
+                                        (grid["num_bin_z"], grid["bin_size_z"], limits[2]))):
+        if L == 0:
+            continue
+        edges = np.arange(nb) * bs
+        cand = np.concatenate([edges, np.nextafter(edges.astype(np.float32), np.float32(np.inf)).astype(np.float64),
+                               np.nextafter(edges[1:].astype(np.float32), np.float32(-np.inf)).astype(np.float64),
+                               [np.nextafter(np.float32(L), np.float32(0))]])
+        cand = cand.astype(np.float32).astype(np.float64)
+        cand = cand[(cand >= 0) & (cand < L)]
+        m = min(len(cand), pos.shape[1] - k)
+        pos[axis, k:k + m] = cand[:m]
+        k += m
+    st["pos"] = f32_state(pos)
+    check_bins_against_oracle(gof, st)
+
+
+def run_accelerator(gof, st, bins, wrap_mode, with_boid_outputs=True):
+    d, pb, cnt, off, stt, idx = bins
+    n, T = st["n"], st["T"]
+    v = [gof.dev.to_device(st["vel"][k]) for k in range(3)]
+    types = gof.dev.to_device(st["types"])
+    f32, i32 = gof.torch.float32, gof.torch.int32
+    acc = [gof.dev.device_array(n, f32) for _ in range(3)]
+    if with_boid_outputs:
+        boid = [gof.dev.device_array(n * T, f32) for _ in range(6)]
+        bc = gof.dev.device_array(n * T, i32)
+    else:
+        boid, bc = [None] * 6, None
+    L = st["limits"]
+    gof.au.accelerator(d[0], d[1], d[2], v[0], v[1], v[2], L[0], L[1], L[2], st["r_max"], n,
+                       st["parameter_matrix"], types, acc[0], acc[1], acc[2], T, *boid, bc, None,
+                       pb, idx, stt, cnt, wrap_mode=wrap_mode)
+    got = np.stack([a.copy_to_host() for a in acc])
+    return got, boid, bc
+
+
+def check_accelerator(gof, st, wrap_mode):
+    o, bins = check_bins_against_oracle(gof, st)
+    o.wrap_mode = wrap_mode
+    o.accelerate()
+    got, boid, bc = run_accelerator(gof, st, bins, wrap_mode)
+    want = np.stack([o.acc_x, o.acc_y, o.acc_z])
+    assert np.array_equal(bc.copy_to_host(), o.boid_counts), "boid neighbour counts must be exact"
+    mx, rms = acc_errors(got, want)
+    assert mx <= ACC_RTOL, f"acceleration error {mx:.3e} (rms {rms:.3e})"
+    if np.any(st["parameter_matrix"][-1] == 1):
+        for k in range(3):
+            np.testing.assert_allclose(boid[3 + k].copy_to_host(), o.boid[3 + k], rtol=1e-4, atol=1e-3)
+            np.testing.assert_allclose(boid[k].copy_to_host(), o.boid[k], rtol=1e-4, atol=1e-2)
+    return mx, rms
+
+
+@pytest.mark.parametrize("wrap_mode", [orc.WRAP_REFERENCE, orc.WRAP_MINIMAGE], ids=["refwrap", "minimage"])
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_accelerator_on_golden_states(gof, path, wrap_mode):
+    _, _, steps = golden_state(path, 0)
+    for s in (0, steps - 1):  # the last recorded state has non-zero velocities (alignment, projection)
+        st, _, _ = golden_state(path, s)
+        check_accelerator(gof, st, wrap_mode)
+
+
+@pytest.mark.parametrize("wrap_mode", [orc.WRAP_REFERENCE, orc.WRAP_MINIMAGE], ids=["refwrap", "minimage"])
+@pytest.mark.parametrize("kinds,counts,limits,speed", [
+    ("clusters", [3000] * 3, (100, 100, 0), 0.0),
+    ("clusters", [4000] * 5, (120, 110, 130), 3.0),
+    ("boids", [5000] * 3, (60, 70, 80), 9.0),
+    ("boids", [3000] * 2, (90, 90, 0), 12.0),
+    ("mixed", [2500] * 6, (110, 110, 110), 8.0),
+    ("mixed", [1200] * 8, (100, 100, 100), 8.0),
+])
+def test_accelerator_random_states(gof, kinds, counts, limits, speed, wrap_mode):
+    st = random_state(counts, limits, seed=11, kinds=kinds, speed=speed)
+    check_accelerator(gof, st, wrap_mode)
+
+
+def engine_from_state(gof, st, wrap_mode=orc.WRAP_REFERENCE):
+    e = gof.eng.ParticleEngine(st["n"], st["parameter_matrix"], st["limits"], st["r_max"], wrap_mode=wrap_mode)
+    e.upload([st["pos"][k].astype(np.float32) for k in range(3)], st["types"],
+             vel=[st["vel"][k].astype(np.float32) for k in range(3)],
+             acc=[st["acc"][k].astype(np.float32) for k in range(3)])
+    return e
+
+
+def check_engine_step(gof, st, ts, wrap_mode=orc.WRAP_REFERENCE):
+    o = oracle_sim(st, timestep=ts, wrap_mode=wrap_mode)
+    used = o.core_step()
+    e = engine_from_state(gof, st, wrap_mode)
+    e.step(1, ts)
+    out = e.download(pos=True, vel=True, acc=True)
+    pb, cnt, stt, idx = e.read_bins()
+    cells = o.grid["num_cells"]
+    assert np.array_equal(pb, o.particle_bins)
+    assert np.array_equal(cnt, o.particle_bin_counts[:cells])
+    assert np.array_equal(stt, o.particle_bin_starts[:cells])
+    assert np.array_equal(idx, o.particle_indices)
+    assert e.last_timestep() == pytest.approx(used, rel=1e-6)
+    mx, rms = acc_errors(out["acc"], np.stack([o.acc_x, o.acc_y, o.acc_z]))
+    assert mx <= ACC_RTOL, f"acceleration error {mx:.3e} (rms {rms:.3e})"
+    # one step of dt <= 0.1 turns an acceleration error e into e*dt in v and e*dt^2/2 in x,
+    # on top of fp32 rounding of the state itself (ulp of a coordinate ~ 1e-5 at 100)
+    a_scale = np.abs(np.stack([o.acc_x, o.acc_y, o.acc_z])).max() + 1.0
+    v_tol = 2e-5 * a_scale * used + 1e-5
+    x_tol = 4 * np.spacing(np.float32(st["limits"].max())) + 1e-5 * a_scale * used * used
+    want_v = np.stack([o.vel_x, o.vel_y, o.vel_z])
+    want_x = np.stack([o.pos_x, o.pos_y, o.pos_z])
+    assert np.abs(out["vel"] - want_v).max() <= v_tol
+    dx = np.abs(out["pos"] - want_x)
+    # a particle that lands within rounding of the wall may or may not have wrapped
+    L = st["limits"][:, None]
+    dx = np.where(L > 0, np.minimum(dx, np.abs(L - dx)), dx)
+    assert dx.max() <= x_tol
+    e.close()
+    return mx
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_engine_step_on_golden_states(gof, path):
+    _, ts, steps = golden_state(path, 0)
+    for s in (0, steps - 1):
+        st, ts, _ = golden_state(path, s)
+        check_engine_step(gof, st, ts)
+
+
+@pytest.mark.parametrize("kinds,counts,limits,speed,ts", [
+    ("clusters", [20000] * 5, (190, 190, 190), 2.0, None),   # BASELINE density 0.014 / unit^3
+    ("clusters", [5000] * 3, (270, 270, 0), 2.0, 0.02),
+    ("boids", [20000] * 3, (160, 160, 160), 9.0, None),
+    ("mixed", [8000] * 8, (165, 165, 165), 6.0, None),
+])
+def test_engine_step_random_states(gof, kinds, counts, limits, speed, ts):
+    st = random_state(counts, limits, seed=23, kinds=kinds, speed=speed)
+    check_engine_step(gof, st, ts)
+    check_engine_step(gof, st, ts, wrap_mode=orc.WRAP_MINIMAGE)
+
+
+def test_engine_is_deterministic_and_keeps_every_particle(gof):
+    st = random_state([30000] * 5, (220, 220, 220), seed=5, kinds="clusters", speed=1.0)
+    outs = []
+    for _ in range(2):
+        e = engine_from_state(gof, st)
+        e.step(5)
+        outs.append(e.download(pos=True, vel=True, acc=True))
+        pb, cnt, stt, idx = e.read_bins()
+        assert np.array_equal(np.sort(idx), np.arange(st["n"])), "ids must stay a permutation"
+        assert cnt.sum() == st["n"]
+        assert np.all(np.diff(pb[idx]) >= 0), "particle_indices must be sorted by cell"
+        e.close()
+    for k in ("pos", "vel", "acc"):
+        assert np.array_equal(outs[0][k], outs[1][k]), f"{k} differs between identical runs"
+    L = st["limits"][:, None]
+    assert np.all(outs[0]["pos"] >= 0) and np.all(outs[0]["pos"] <= L)
+
+
+def test_engine_trajectory_statistics_against_oracle(gof):
+    """Trajectories are chaotic: after many steps compare distributions, not particles."""
+    st = random_state([4000] * 3, (150, 150, 0), seed=3, kinds="clusters")
+    o = oracle_sim(st, timestep=None, n_threads=orc.max_threads())
+    e = engine_from_state(gof, st)
+    steps = 60
+    for _ in range(steps):
+        o.core_step()
+    e.step(steps)
+    out = e.download(pos=True, vel=True)
+    spd_g = np.linalg.norm(out["vel"], axis=0)
+    spd_o = np.linalg.norm(np.stack([o.vel_x, o.vel_y, o.vel_z]), axis=0)
+    assert spd_g.mean() == pytest.approx(spd_o.mean(), rel=0.05)
+    assert np.percentile(spd_g, 90) == pytest.approx(np.percentile(spd_o, 90), rel=0.1)
+    # cell occupancy histogram (clustering) agrees
+    pb, cnt, _, _ = e.read_bins()
+    o.setup_bins()
+    co = o.particle_bin_counts[:o.grid["num_cells"]]
+    assert np.std(cnt) == pytest.approx(np.std(co), rel=0.15)
+    e.close()
+
+
+def test_simulation_class_drop_in(gof, tmp_path):
+    """The reference's Simulation surface: update(), output, update_parameter_matrix, blind_run + record."""
+    from game_of_flies_b200.simulation import Simulation
+    sim = Simulation(np.array([300, 300]), np.array([200]), seed=434, limits=(100, 100, 100))
+    p0 = np.stack([sim.pos_x, sim.pos_y, sim.pos_z]).copy()
+    sim.update()
+    assert sim.output.shape == (800, 3) and sim.output.dtype == np.float64
+    assert np.abs(sim.output.T - p0).max() < 1.0  # one small step from the initial positions
+    assert not np.array_equal(sim.output.T, p0)
+    params = [6.0, 11.0, -9.0, 3.0, 0]
+    sim.update_parameter_matrix(0, 1, params)
+    assert np.array_equal(sim.parameter_matrix[:, 0, 1], params)
+    sim.update()
+    rec = str(tmp_path / "run")
+    sim.blind_run(3, rec)
+    frames = sorted(os.listdir(os.path.join(rec, "frames")))
+    assert frames == ["00000.npy", "00001.npy", "00002.npy", "00003.npy"]
+    state = np.load(os.path.join(rec, "state.npz"))
+    assert int(state["num_particles"]) == 800 and state["type_array"].shape == (800,)
+    f = np.load(os.path.join(rec, "frames", "00003.npy"))
+    assert f.shape == (800, 3)
+
+
+def test_full_size_properties_clusters3d_1m(gof):
+    """BASELINE.json configs[1] (Clusters 3D, 5 species, N=1M): size-independent properties."""
+    n_per = 200_000
+    L = float((5 * n_per / 0.014) ** (1.0 / 3.0))
+    st = random_state([n_per] * 5, (L, L, L), seed=1, kinds="clusters")
+    e = engine_from_state(gof, st)
+    e.step(2)
+    pb, cnt, stt, idx = e.read_bins()
+    n = st["n"]
+    assert cnt.sum() == n
+    assert np.array_equal(stt, np.concatenate([[0], np.cumsum(cnt)[:-1]]))
+    assert np.array_equal(np.sort(idx), np.arange(n))
+    assert np.all(np.diff(pb[idx]) >= 0)
+    # stable inside every cell: ids ascending wherever the cell does not change
+    same = np.diff(pb[idx]) == 0
+    assert np.all(np.diff(idx)[same] > 0)
+    out = e.download(pos=True, vel=True, acc=True)
+    assert np.all(np.isfinite(out["acc"])) and np.all(np.isfinite(out["pos"]))
+    # a random sample of particles against a brute-force float64 evaluation of the same state
+    e2 = engine_from_state(gof, st)
+    e2.accelerate()
+    acc = e2.download(pos=False, acc=True)["acc"]
+    rng = np.random.default_rng(0)
+    sample = rng.choice(n, 64, replace=False)
+    pos = st["pos"]
+    pm = st["parameter_matrix"]
+    Lv = st["limits"]
+    for i in sample:
+        d = pos[:, i:i + 1] - pos
+        d -= Lv[:, None] * np.round(d / Lv[:, None])
+        r2 = (d * d).sum(0)
+        m = (r2 > 1e-10) & (r2 < st["r_max"] ** 2)
+        r = np.sqrt(r2[m])
+        tj = st["types"][m]
+        a0, a1, a2, a3 = (pm[k, st["types"][i], tj] for k in range(4))
+        f = np.where(r < a0, -a2 / a0 * r + a2,
+                     np.where(r < (a0 + a1) / 2, 2 * a3 / (a1 - a0) * (r - a0), 2 * a3 / (a1 - a0) * (a1 - r)))
+        want = -(f / r * d[:, m]).sum(1)
+        z_edge = pos[2, i] < st["r_max"] or pos[2, i] > Lv[2] - st["r_max"] or pos[1, i] > Lv[2] - st["r_max"]
+        if z_edge:
+            continue  # the reference's z-wrap quirk applies there; covered by the oracle tests
+        assert np.linalg.norm(acc[:, i] - want) <= 1e-5 * max(np.linalg.norm(want), 10.0)
+    e.close(); e2.close()
