@@ -70,6 +70,8 @@ SIGNATURES = {
     "gof_engine_download": (_i, [_vp] + [_vp] * 9 + [_vp]),
     "gof_engine_snapshot": (_i, [_vp, _vp, _vp]),
     "gof_engine_read_bins": (_i, [_vp] + [_vp] * 4 + [_vp]),
+    "gof_engine_timing": (_i, [_vp, _i]),
+    "gof_engine_force_time": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
     "gof_engine_last_timestep": (_i, [_vp, C.POINTER(_f), _vp]),
 }
 

@@ -672,7 +672,14 @@ struct gof_engine {
     int* stage_bins = nullptr;     // particle_bins / particle_indices export
     int* stage_indices = nullptr;
     float* stage_xyz = nullptr;    // snapshot [N][3]
+
+    // optional per-launch timing of the force kernel (bench.py roofline)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;  // pairs: start, stop
+    int ev_used = 0;
 };
+
+static constexpr int kMaxTimedLaunches = 4096;
 
 static size_t engine_layout(gof_engine* e, char* base)
 {
@@ -730,7 +737,37 @@ extern "C" int gof_engine_create(gof_engine** out, int device, int num_particles
     return 0;
 }
 
-extern "C" void gof_engine_destroy(gof_engine* e) { delete e; }
+extern "C" void gof_engine_destroy(gof_engine* e)
+{
+    if (!e) return;
+    for (cudaEvent_t v : e->ev) cudaEventDestroy(v);
+    delete e;
+}
+
+extern "C" int gof_engine_timing(gof_engine* e, int enable)
+{
+    if (!e) return fail(GOF_E_INVALID, "null engine");
+    GOF_CUDA(cudaSetDevice(e->device));
+    e->timing = enable != 0;
+    e->ev_used = 0;
+    return 0;
+}
+
+extern "C" int gof_engine_force_time(gof_engine* e, float* total_ms, int* launches)
+{
+    if (!e || !total_ms || !launches) return fail(GOF_E_INVALID, "gof_engine_force_time: null pointer");
+    GOF_CUDA(cudaSetDevice(e->device));
+    float sum = 0.f;
+    for (int k = 0; k < e->ev_used; ++k) {
+        float ms = 0.f;
+        GOF_CUDA(cudaEventSynchronize(e->ev[2 * k + 1]));
+        GOF_CUDA(cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = e->ev_used;
+    return 0;
+}
 
 extern "C" size_t gof_engine_arena_bytes(const gof_engine* e) { return e ? e->arena_bytes : 0; }
 
@@ -855,7 +892,20 @@ extern "C" int gof_engine_step(gof_engine* e, int n_steps, float timestep, int w
         engine_force_args(e, wrap_mode, &a);
         a.integrate = 1;
         a.parity_out = e->parity ^ 1;
+        const bool timed = e->timing && e->ev_used < kMaxTimedLaunches;
+        if (timed) {
+            while ((int)e->ev.size() < 2 * (e->ev_used + 1)) {
+                cudaEvent_t v;
+                GOF_CUDA(cudaEventCreate(&v));
+                e->ev.push_back(v);
+            }
+            GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used], st));
+        }
         if (int rc = launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st)) return rc;
+        if (timed) {
+            GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used + 1], st));
+            ++e->ev_used;
+        }
         e->parity ^= 1;
     }
     return 0;

@@ -62,19 +62,33 @@ struct Home {
 
 // Exact (float64) re-evaluation of the squared distance, in the operation order of
 // the reference (`pos_2 -= limit` first, then `pos[i] - pos_2`, then dx*dx + dy*dy + dz*dz
-// without contraction).  Only reached inside the guard band around r_max^2.
-__device__ __noinline__ bool exact_in_range(const Geometry& g, float xi, float yi, float zi,
-                                            const float4& pj, int sx, int sy, int sz,
-                                            double* dist2_out)
+// without contraction).  Only reached inside the guard band around r_max^2 (and on the
+// edge of a Boids separation radius).  Scalars by value: taking the address of the
+// neighbour's float4 would force it through local memory in the hot loop.
+__device__ __noinline__ double exact_dist2(const Geometry& g, float xi, float yi, float zi,
+                                           float xj, float yj, float zj, int shifts)
 {
-    const double x2 = sx ? __dsub_rn((double)pj.x, sx * g.Lxd) : (double)pj.x;
-    const double y2 = sy ? __dsub_rn((double)pj.y, sy * g.Lyd) : (double)pj.y;
-    const double z2 = sz ? __dsub_rn((double)pj.z, sz * g.Lzd) : (double)pj.z;
+    const int sx = (shifts & 3) - 1, sy = ((shifts >> 2) & 3) - 1, sz = ((shifts >> 4) & 3) - 1;
+    const double x2 = sx ? __dsub_rn((double)xj, sx * g.Lxd) : (double)xj;
+    const double y2 = sy ? __dsub_rn((double)yj, sy * g.Lyd) : (double)yj;
+    const double z2 = sz ? __dsub_rn((double)zj, sz * g.Lzd) : (double)zj;
     const double dx = __dsub_rn((double)xi, x2), dy = __dsub_rn((double)yi, y2),
                  dz = __dsub_rn((double)zi, z2);
-    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    if (dist2_out) *dist2_out = d2;
-    return (1e-10 < d2) && (d2 < g.r2d);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ int pack_shifts(int sx, int sy, int sz)
+{
+    return (sx + 1) | ((sy + 1) << 2) | ((sz + 1) << 4);
+}
+
+// d2 > 1e-10 is guaranteed by the caller, so the flush-to-zero approximate form is safe
+// (a single MUFU.RSQ; plain rsqrtf adds denormal scaling around it).  Max error 2 ulp.
+__device__ __forceinline__ float fast_rsqrt(float v)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
 }
 
 // One accepted pair: add what j does to the home particle.
@@ -82,31 +96,32 @@ __device__ __noinline__ bool exact_in_range(const Geometry& g, float xi, float y
 //   (rx, ry, rz) = neighbour - home as the reference accumulates it for cohesion
 //   exact_d2()   = the float64 squared distance, evaluated only on the edge of r_sep
 template <bool BOIDS, typename ExactD2>
-__device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ tab, int T,
+__device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ tabrow,
                                          float* __restrict__ boid_acc, const ForceArgs& a,
-                                         int j, int tj, float dx, float dy, float dz, float rx,
-                                         float ry, float rz, float d2, ExactD2 exact_d2)
+                                         int T, int j, int tj, float dx, float dy, float dz,
+                                         float rx, float ry, float rz, float d2, ExactD2 exact_d2)
 {
-    const float inv = rsqrtf(d2);
+    const float inv = fast_rsqrt(d2);
     const float dist = d2 * inv;
-    const PairParam q = tab[h.type * T + tj];
+    const float4 qa = tabrow[tj].a;
     if (!BOIDS || !((h.kinds >> tj) & 1u)) {
         // clusters(): piecewise linear profile, force along the separation vector
-        const float f_in = fmaf(-q.a.y, dist, q.a.z);
-        const float f_tri = fmaf(-q.b.x, fabsf(dist - q.a.w), q.b.y);
-        const float s = (dist < q.a.x ? f_in : f_tri) * inv;
+        const float4 qb = tabrow[tj].b;
+        const float f_in = fmaf(-qa.y, dist, qa.z);
+        const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+        const float s = (dist < qa.x ? f_in : f_tri) * inv;
         h.ax = fmaf(-s, dx, h.ax);
         h.ay = fmaf(-s, dy, h.ay);
         h.az = fmaf(-s, dz, h.az);
     } else {
         // boids(): separation inside r_sep, and the per-type sums for cohesion / alignment
-        bool sep = dist < q.a.x;
-        if (fabsf(dist - q.a.x) < 4e-6f * q.a.x) {
+        bool sep = dist < qa.x;
+        if (fabsf(dist - qa.x) < 4e-6f * qa.x) {
             // on the edge of the separation radius the decision is taken in float64
             sep = sqrt(exact_d2()) < a.sep_exact[h.type * T + tj];
         }
         if (sep) {
-            const float s = q.a.y * inv;
+            const float s = qa.y * inv;
             h.ax = fmaf(s, dx, h.ax);
             h.ay = fmaf(s, dy, h.ay);
             h.az = fmaf(s, dz, h.az);
@@ -123,32 +138,152 @@ __device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ 
     }
 }
 
-// A contiguous run [s, e) of neighbour particles seen with one periodic shift
-// (sx, sy, sz) in {-1, 0, 1}: the home particle is moved by shift * L so that
-// `home - neighbour` is the minimum-image separation.
-template <bool BOIDS>
-__device__ __forceinline__ void run_pairs(Home& h, const PairParam* __restrict__ tab, int T,
-                                          float* __restrict__ boid_acc, const ForceArgs& a,
-                                          const Geometry& g, int s, int e, int sx, int sy, int sz)
+// The periodic image of the home particle that a run of neighbours sees: home + s * L
+// per axis, s in {-1, 0, 1}.  Subtracting L from a coordinate near L is exact; ADDING L to
+// a small coordinate rounds away its low bits, the same way for every pair of the run, so
+// a particle next to the lower wall would collect a systematic error.  `lo` holds what the
+// rounded sum lost (two-sum); runs that shifted upwards add it back per pair (LOWFIX).
+struct Image {
+    float x, y, z;     // rounded home + s * L
+    float lx, ly, lz;  // exact remainder of that sum
+    int shifts;        // packed (sx, sy, sz)
+    bool up;           // some axis was shifted upwards
+};
+
+__device__ __forceinline__ void shifted(float v, int s, float L, float& hi, float& lo)
 {
-    const float xs = h.x + sx * g.Lx, ys = h.y + sy * g.Ly, zs = h.z + sz * g.Lz;
-#pragma unroll 2
-    for (int j = s; j < e; ++j) {
-        const float4 pj = ldg4(a.posw + j);
-        const float dx = xs - pj.x, dy = ys - pj.y, dz = zs - pj.z;
-        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d2 < g.r2_hi && d2 > 1e-10f) {
-            bool ok = true;
-            if (d2 > g.r2_lo) ok = exact_in_range(g, h.x, h.y, h.z, pj, sx, sy, sz, nullptr);
-            if (ok)
-                interact<BOIDS>(h, tab, T, boid_acc, a, j, __float_as_int(pj.w), dx, dy, dz, -dx,
-                                -dy, -dz, d2, [&]() {
-                                    double d2d;
-                                    exact_in_range(g, h.x, h.y, h.z, pj, sx, sy, sz, &d2d);
-                                    return d2d;
-                                });
+    const float t = s * L;
+    hi = v + t;
+    const float bb = hi - v;
+    lo = (v - (hi - bb)) + (t - bb);
+}
+
+__device__ __forceinline__ Image make_image(const Home& h, const Geometry& g, int sx, int sy, int sz)
+{
+    Image im;
+    shifted(h.x, sx, g.Lx, im.x, im.lx);
+    shifted(h.y, sy, g.Ly, im.y, im.ly);
+    shifted(h.z, sz, g.Lz, im.z, im.lz);
+    im.shifts = pack_shifts(sx, sy, sz);
+    im.up = (sx > 0) | (sy > 0) | (sz > 0);
+    return im;
+}
+
+__device__ __forceinline__ float4 lds4(unsigned saddr)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float2 lds2(unsigned saddr)
+{
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+    return v;
+}
+
+// A pair inside the guard band of r_max^2, Clusters kind: decided in float64, out of line.
+__device__ __noinline__ float3 band_pair_clusters(const Geometry& g, float xi, float yi, float zi,
+                                                  float xj, float yj, float zj, int shifts,
+                                                  float dx, float dy, float dz, float d2,
+                                                  float4 qa, float2 qb)
+{
+    const double e = exact_dist2(g, xi, yi, zi, xj, yj, zj, shifts);
+    if (!((1e-10 < e) && (e < g.r2d))) return make_float3(0.f, 0.f, 0.f);
+    const float inv = fast_rsqrt(d2);
+    const float dist = d2 * inv;
+    const float f_in = fmaf(-qa.y, dist, qa.z);
+    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+    const float s = (dist < qa.x ? f_in : f_tri) * inv;
+    return make_float3(-s * dx, -s * dy, -s * dz);
+}
+
+// Distance test + interaction of one neighbour.
+//  BOIDS = false: every species pair is of the Clusters kind.  With ~830 candidates and
+//  ~130 neighbours per particle at least one lane of a warp accepts almost every candidate,
+//  so a branch around the force evaluation never skips it; it only adds divergence
+//  bookkeeping and serialises the loop.  The evaluation is therefore done for every
+//  candidate and masked: 23 issue slots per candidate instead of ~33, no divergence.
+//  BOIDS = true: the per-type sums make the accepted path long; it stays behind a branch.
+template <bool BOIDS, bool LOWFIX>
+__device__ __forceinline__ void pair(Home& h, unsigned tabrow_s, const PairParam* __restrict__ tabrow,
+                                     float* __restrict__ boid_acc, const ForceArgs& a,
+                                     const Geometry& g, const Image& im, int j, const float4 pj)
+{
+    float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
+    if (LOWFIX) { dx += im.lx; dy += im.ly; dz += im.lz; }
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const bool in = d2 < g.r2_hi && d2 > 1e-10f;
+    if (!BOIDS) {
+        const bool band = in && d2 > g.r2_lo;
+        const unsigned qaddr = tabrow_s + (unsigned)__float_as_int(pj.w) * (unsigned)sizeof(PairParam);
+        const float4 qa = lds4(qaddr);
+        const float2 qb = lds2(qaddr + 16);
+        const float inv = fast_rsqrt(d2);  // inf for the self pair: masked below
+        const float dist = d2 * inv;
+        const float f_in = fmaf(-qa.y, dist, qa.z);
+        const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+        float s = (dist < qa.x ? f_in : f_tri) * inv;
+        s = (in && !band) ? s : 0.0f;
+        h.ax = fmaf(-s, dx, h.ax);
+        h.ay = fmaf(-s, dy, h.ay);
+        h.az = fmaf(-s, dz, h.az);
+        if (band) {
+            const float3 f = band_pair_clusters(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts, dx, dy,
+                                                dz, d2, qa, qb);
+            h.ax += f.x; h.ay += f.y; h.az += f.z;
         }
+    } else if (in) {
+        bool ok = true;
+        if (d2 > g.r2_lo) {
+            const double e = exact_dist2(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts);
+            ok = (1e-10 < e) && (e < g.r2d);
+        }
+        if (ok)
+            interact<BOIDS>(h, tabrow, boid_acc, a, a.T, j, __float_as_int(pj.w), dx, dy, dz, -dx,
+                            -dy, -dz, d2,
+                            [&]() { return exact_dist2(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts); });
     }
+}
+
+// A contiguous run [s, e) of neighbour particles seen through one periodic image.
+// Four independent 16-byte loads are issued before the four tests that consume them, so
+// the L1 latency of a neighbour is hidden behind the arithmetic of the previous ones.
+template <bool BOIDS, bool LOWFIX>
+__device__ __forceinline__ void run_pairs(Home& h, unsigned tabrow_s,
+                                          const PairParam* __restrict__ tabrow,
+                                          float* __restrict__ boid_acc, const ForceArgs& a,
+                                          const Geometry& g, const Image& im, int s, int e)
+{
+    // the run sums into its own accumulator (shorter partial sums: less fp32 rounding)
+    const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+    h.ax = h.ay = h.az = 0.0f;
+    int j = s;
+    for (; j + 4 <= e; j += 4) {
+        const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
+                     p3 = ldg4(a.posw + j + 3);
+        pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j, p0);
+        pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 1, p1);
+        pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 2, p2);
+        pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 3, p3);
+    }
+    for (; j < e; ++j) pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j, ldg4(a.posw + j));
+    h.ax += ax0; h.ay += ay0; h.az += az0;
+}
+
+// Warp-uniform choice of the LOWFIX variant: callers are convergent (every lane walks the
+// same sequence of runs, possibly empty), so the vote is safe and costs no divergence.
+template <bool BOIDS>
+__device__ __forceinline__ void run_image(Home& h, unsigned tabrow_s,
+                                          const PairParam* __restrict__ tabrow,
+                                          float* __restrict__ boid_acc, const ForceArgs& a,
+                                          const Geometry& g, int sx, int sy, int sz, int s, int e)
+{
+    const Image im = make_image(h, g, sx, sy, sz);
+    if (__any_sync(0xffffffffu, im.up && e > s))
+        run_pairs<BOIDS, true>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
+    else
+        run_pairs<BOIDS, false>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
 }
 
 // The reference's z wrap (acceleration_updater.py:325-328) tests pos_y[i] where it
@@ -159,12 +294,12 @@ __device__ __forceinline__ void run_pairs(Home& h, const PairParam* __restrict__
 //   direct : the home particle is the reference's thread i, the neighbour its j
 //   !direct: the neighbour is thread i and updated the home particle as its j
 template <bool BOIDS>
-__device__ __noinline__ void run_pairs_zquirk(Home& h, const PairParam* __restrict__ tab, int T,
+__device__ __noinline__ void run_pairs_zquirk(Home& h, const PairParam* __restrict__ tabrow,
                                               float* __restrict__ boid_acc, const ForceArgs& a,
                                               const Geometry& g, int s, int e, int sx, int sy,
                                               bool direct)
 {
-    const float xs = h.x + sx * g.Lx, ys = h.y + sy * g.Ly;
+    const Image im = make_image(h, g, sx, sy, 0);
     const double R = g.rmaxd, Lz = g.Lzd, top = g.Lzd - g.rmaxd;
     for (int j = s; j < e; ++j) {
         const float4 pj = ldg4(a.posw + j);
@@ -186,13 +321,14 @@ __device__ __noinline__ void run_pairs_zquirk(Home& h, const PairParam* __restri
             else if (zw < R && zi > top) zw += Lz;
             relz = zw - zi;
         }
-        const float dx = xs - pj.x, dy = ys - pj.y, dz = (float)dzd;
+        const float dx = (im.x - pj.x) + im.lx, dy = (im.y - pj.y) + im.ly, dz = (float)dzd;
         const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         if (d2 < g.r2_hi && d2 > 1e-10f) {
+            const float hx = h.x, hy = h.y, pjx = pj.x, pjy = pj.y;
             auto exact = [&]() {
-                const double x2 = sx ? __dsub_rn((double)pj.x, sx * g.Lxd) : (double)pj.x;
-                const double y2 = sy ? __dsub_rn((double)pj.y, sy * g.Lyd) : (double)pj.y;
-                const double ddx = __dsub_rn((double)h.x, x2), ddy = __dsub_rn((double)h.y, y2);
+                const double x2 = sx ? __dsub_rn((double)pjx, sx * g.Lxd) : (double)pjx;
+                const double y2 = sy ? __dsub_rn((double)pjy, sy * g.Lyd) : (double)pjy;
+                const double ddx = __dsub_rn((double)hx, x2), ddy = __dsub_rn((double)hy, y2);
                 return __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
                                  __dmul_rn(dzd, dzd));
             };
@@ -202,14 +338,14 @@ __device__ __noinline__ void run_pairs_zquirk(Home& h, const PairParam* __restri
                 ok = (1e-10 < d2d) && (d2d < g.r2d);
             }
             if (ok)
-                interact<BOIDS>(h, tab, T, boid_acc, a, j, __float_as_int(pj.w), dx, dy, dz, -dx,
-                                -dy, (float)relz, d2, exact);
+                interact<BOIDS>(h, tabrow, boid_acc, a, a.T, j, __float_as_int(pj.w), dx, dy, dz,
+                                -dx, -dy, (float)relz, d2, exact);
         }
     }
 }
 
 template <bool BOIDS, int MODE>
-__global__ void __launch_bounds__(kForceThreads)
+__global__ void __launch_bounds__(kForceThreads, 5)
 k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
 {
     extern __shared__ float4 smem_raw[];
@@ -234,6 +370,8 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     h.ax = h.ay = h.az = 0.0f;
     h.type = __float_as_int(pi.w);
     h.kinds = BOIDS ? a.kind_rows[h.type] : 0u;
+    const PairParam* tabrow = tab + h.type * T;
+    const unsigned tabrow_s = (unsigned)__cvta_generic_to_shared(tabrow);
 
     const int c = a.cell_sorted[k];
     const int cx = c % g.nbx;
@@ -267,14 +405,14 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 int s = a.start[rb + lo];
                 int e = a.start[rb + hi] + a.count[rb + hi];
                 if (!valid) e = s;
-                run_pairs<BOIDS>(h, tab, T, boid_acc, a, g, s, e, 0, sy, sz);
-                // the cell across the periodic x boundary, if the home cell is on the edge
-                if (cx == 0 || cx == g.nbx - 1) {
-                    const int wc = cx == 0 ? g.nbx - 1 : 0;
-                    s = a.start[rb + wc];
-                    e = valid ? s + a.count[rb + wc] : s;
-                    run_pairs<BOIDS>(h, tab, T, boid_acc, a, g, s, e, cx == 0 ? 1 : -1, sy, sz);
-                }
+                run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, 0, sy, sz, s, e);
+                // the cell across the periodic x boundary (an empty run for interior home cells:
+                // every lane makes the same calls, so the warp votes inside stay convergent)
+                const bool xedge = cx == 0 || cx == g.nbx - 1;
+                const int wc = cx == 0 ? g.nbx - 1 : 0;
+                s = a.start[rb + wc];
+                e = (valid && xedge) ? s + a.count[rb + wc] : s;
+                run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e);
             }
         }
     } else {
@@ -298,7 +436,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                     const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
                     const int s = a.start[rb + nx];
                     const int e = valid ? s + a.count[rb + nx] : s;
-                    run_pairs_zquirk<BOIDS>(h, tab, T, boid_acc, a, g, s, e, sx, sy, direct);
+                    run_pairs_zquirk<BOIDS>(h, tabrow, boid_acc, a, g, s, e, sx, sy, direct);
                 }
             }
         }

@@ -144,3 +144,27 @@ class ParticleEngine:
         out = C.c_float()
         _lib.check(self.lib.gof_engine_last_timestep(self._handle, C.byref(out), self._stream()))
         return float(out.value)
+
+    def timing(self, enable: bool):
+        """Bracket every force-kernel launch with CUDA events (bench.py roofline)."""
+        _lib.check(self.lib.gof_engine_timing(self._handle, 1 if enable else 0))
+
+    def force_time(self):
+        """(total milliseconds, launches) of the force kernel since timing(True)."""
+        ms, k = C.c_float(), C.c_int()
+        _lib.check(self.lib.gof_engine_force_time(self._handle, C.byref(ms), C.byref(k)))
+        return float(ms.value), int(k.value)
+
+    def candidate_pairs(self) -> int:
+        """Distance tests the force kernel performs for the current binning: for every particle
+        the population of its 9 / 27 stencil cells (host arithmetic on the cell counts)."""
+        _, cnt, _, _ = self.read_bins()
+        g = self.grid
+        nz = max(int(g.num_bin_z), 1)
+        c = cnt.astype(np.int64).reshape(nz, int(g.num_bin_y), int(g.num_bin_x))
+        nb = np.zeros_like(c)
+        for dz in ((-1, 0, 1) if g.num_bin_z > 0 else (0,)):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    nb += np.roll(c, (dz, dy, dx), axis=(0, 1, 2))
+        return int((c * nb).sum())

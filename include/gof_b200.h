@@ -183,6 +183,13 @@ int gof_engine_snapshot(gof_engine *e, float *xyz_any, void *stream);
 int gof_engine_read_bins(gof_engine *e, int32_t *particle_bins_any, int32_t *bin_counts_any,
                          int32_t *bin_starts_any, int32_t *particle_indices_any, void *stream);
 
+/* Per-kernel timing for bench.py's roofline: when enabled, gof_engine_step brackets every
+ * force-kernel launch with CUDA events on `stream` (up to 4096 launches per enable).
+ * gof_engine_force_time synchronises on the recorded events and returns the summed
+ * device time in milliseconds and the number of launches it covers. */
+int gof_engine_timing(gof_engine *e, int enable);
+int gof_engine_force_time(gof_engine *e, float *total_ms, int *launches);
+
 /* The timestep the last step used (synchronises `stream`). */
 int gof_engine_last_timestep(gof_engine *e, float *out, void *stream);
 

@@ -36,8 +36,15 @@ def random_state(n_per_type, limits, seed, kinds="clusters", speed=0.0):
         for i in range(h):
             for j in range(h, T):
                 kind[i, j] = kind[j, i] = float(rng.random() > 0.5)
-    u = rng.random((4, T, T))
+    # parameter planes drawn like the reference's rand_param_matrix (state_parameters.py:5-36):
+    # planes 0 and 1 come from ONE sorted pool, so every r_min lies below every r_max
+    pool = rng.random(4 * T * T)
+    pool[: 2 * T * T].sort()
+    rng.shuffle(pool[: T * T])
+    rng.shuffle(pool[T * T: 2 * T * T])
+    u = pool.reshape(4, T, T)
     clus = kind == 0
+    # scaling of Simulation.__init__ (simulation.py:70-96)
     pm[0] = np.where(clus, 5 + 3 * u[0], 12 + 2 * u[0])
     pm[1] = np.where(clus, 8 + 5 * u[1], 2 + 4 * u[1])
     pm[2] = np.where(clus, -10 + 3 * u[2], 2 + 2 * u[2])

@@ -277,10 +277,12 @@ def test_simulation_class_drop_in(gof, tmp_path):
     rec = str(tmp_path / "run")
     sim.blind_run(3, rec)
     frames = sorted(os.listdir(os.path.join(rec, "frames")))
-    assert frames == ["00000.npy", "00001.npy", "00002.npy", "00003.npy"]
+    # like the reference (simulation.py:328-345): the initial frame 00000 is overwritten by the
+    # first step's frame because `frame` is only advanced inside the loop
+    assert frames == ["00000.npy", "00001.npy", "00002.npy"]
     state = np.load(os.path.join(rec, "state.npz"))
     assert int(state["num_particles"]) == 800 and state["type_array"].shape == (800,)
-    f = np.load(os.path.join(rec, "frames", "00003.npy"))
+    f = np.load(os.path.join(rec, "frames", "00002.npy"))
     assert f.shape == (800, 3)
 
 
