@@ -79,7 +79,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB
+    """The in-tree library; GOF_B200_LIB selects another build of it (kernel tuning sweeps)."""
+    return os.environ.get("GOF_B200_LIB") or _build.LIB
 
 
 def load() -> C.CDLL:
@@ -88,7 +89,7 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = library_path()
-    if _build.stale():
+    if path == _build.LIB and _build.stale():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on this host

@@ -263,7 +263,9 @@ static int upload_species(const HostSpecies& h, const DeviceSpecies& d, cudaStre
 
 static size_t force_smem_bytes(int T, bool boids)
 {
-    return (size_t)T * T * sizeof(PairParam) + (boids ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0);
+    const size_t TA = (size_t)(T | 1);
+    return (size_t)T * T * sizeof(PairParam) + (size_t)T * TA * (sizeof(float4) + sizeof(float2)) + 16 +
+           (boids ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0);
 }
 
 template <bool BOIDS, int MODE>

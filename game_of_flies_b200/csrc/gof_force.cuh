@@ -17,6 +17,10 @@
 #pragma once
 #include "gof_binning.cuh"
 
+#ifndef GOF_FORCE_PREFETCH
+#define GOF_FORCE_PREFETCH 1
+#endif
+
 namespace gof {
 
 constexpr int kForceThreads = 128;
@@ -169,6 +173,14 @@ __device__ __forceinline__ Image make_image(const Home& h, const Geometry& g, in
     return im;
 }
 
+// Shared-memory addresses of the home type's rows in the split parameter arrays used by
+// the hot Clusters loop: A holds {r_min, k0, f_min, mid} (16 B), B holds {s1, f_max} (8 B).
+// Lanes of a warp have different home types but (mostly) the same neighbour type, so they
+// read up to T different rows at once.  The row stride is an ODD number of entries, which
+// puts the rows of any <= 8 (A) / 16 (B) home types on different banks: one wavefront per
+// load instead of the 3+ the 32-byte AoS rows cost.
+struct RowAddr { unsigned a, b; };
+
 __device__ __forceinline__ float4 lds4(unsigned saddr)
 {
     float4 v;
@@ -182,20 +194,89 @@ __device__ __forceinline__ float2 lds2(unsigned saddr)
     return v;
 }
 
-// A pair inside the guard band of r_max^2, Clusters kind: decided in float64, out of line.
-__device__ __noinline__ float3 band_pair_clusters(const Geometry& g, float xi, float yi, float zi,
-                                                  float xj, float yj, float zj, int shifts,
-                                                  float dx, float dy, float dz, float d2,
-                                                  float4 qa, float2 qb)
+constexpr float kTinyD2 = 1e-30f;  // keeps rsqrt finite for the self pair (whose separation is exactly 0)
+
+// Cold path of the Clusters loop: a pair inside the guard band of r_max^2, or closer
+// than the reference's 1e-10 lower bound.  The hot loop added the pair's force iff its
+// fp32 d2 was below r2_lo; here the reference's float64 decision is taken and the
+// difference returned.  Recomputes the fp32 separation exactly as the hot loop does (the
+// `lo` parts are zero for images that were not shifted upwards).
+__device__ __noinline__ float3 repair_pair_clusters(const Geometry& g, float xi, float yi, float zi,
+                                                    float imx, float imy, float imz, float lx,
+                                                    float ly, float lz, int shifts, float xj,
+                                                    float yj, float zj, const PairParam* q)
 {
+    const float dx = (imx - xj) + lx, dy = (imy - yj) + ly, dz = (imz - zj) + lz;
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const bool added = d2 < g.r2_lo;
     const double e = exact_dist2(g, xi, yi, zi, xj, yj, zj, shifts);
-    if (!((1e-10 < e) && (e < g.r2d))) return make_float3(0.f, 0.f, 0.f);
-    const float inv = fast_rsqrt(d2);
+    const bool wanted = (1e-10 < e) && (e < g.r2d);
+    if (added == wanted) return make_float3(0.f, 0.f, 0.f);
+    const float4 qa = q->a;
+    const float4 qb = q->b;
+    const float inv = fast_rsqrt(d2 + kTinyD2);
     const float dist = d2 * inv;
     const float f_in = fmaf(-qa.y, dist, qa.z);
     const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-    const float s = (dist < qa.x ? f_in : f_tri) * inv;
+    float s = (dist < qa.x ? f_in : f_tri) * inv;
+    if (added) s = -s;  // take it back
     return make_float3(-s * dx, -s * dy, -s * dz);
+}
+
+// The species-pair parameters of the neighbour type seen last, kept in registers.
+// Particles are ordered by id inside a cell and the reference numbers its particles
+// species by species (state_parameters.py:76-81), so a run of neighbours changes type
+// only a few times: the two shared-memory loads below are predicated off for ~85% of the
+// pairs.  That matters because the SM returns at most 128 B/clk from L1/shared to the
+// register file: 16 B of neighbour + 24 B of parameters per lane and pair made that path,
+// not the issue slots, the limiter.
+struct ParamCache {
+    int t;
+    float4 qa;
+    float2 qb;
+};
+
+// Branch-free Clusters pair (see `pair` below).  Adds the force iff d2 < r2_lo and
+// returns d2 so that the caller can spot the rare pairs that need the cold path.
+template <bool LOWFIX>
+__device__ __forceinline__ float pair_clusters(Home& h, ParamCache& pc, RowAddr tabrow_s,
+                                               const Geometry& g, const Image& im, const float4 pj)
+{
+    float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
+    if (LOWFIX) { dx += im.lx; dy += im.ly; dz += im.lz; }
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const int tj = __float_as_int(pj.w);
+    if (tj != pc.t) {
+        pc.t = tj;
+        pc.qa = lds4(tabrow_s.a + (unsigned)tj * 16u);
+        pc.qb = lds2(tabrow_s.b + (unsigned)tj * 8u);
+    }
+    const float4 qa = pc.qa;
+    const float2 qb = pc.qb;
+    const float inv = fast_rsqrt(d2 + kTinyD2);
+    const float dist = d2 * inv;
+    const float f_in = fmaf(-qa.y, dist, qa.z);
+    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+    float s = (dist < qa.x ? f_in : f_tri) * inv;
+    s = d2 < g.r2_lo ? s : 0.0f;
+    h.ax = fmaf(-s, dx, h.ax);  // the self pair contributes s * 0 = 0 with s finite
+    h.ay = fmaf(-s, dy, h.ay);
+    h.az = fmaf(-s, dz, h.az);
+    return d2;
+}
+
+// needs the cold path: in the guard band, or at/below the reference's 1e-10 bound
+__device__ __forceinline__ bool needs_repair(const Geometry& g, float d2)
+{
+    return (!(d2 < g.r2_lo) && d2 < g.r2_hi) || d2 <= 1e-10f;
+}
+
+__device__ __forceinline__ void repair(Home& h, const PairParam* __restrict__ tabrow,
+                                       const Geometry& g, const Image& im, const float4 pj)
+{
+    const float3 f = repair_pair_clusters(g, h.x, h.y, h.z, im.x, im.y, im.z, im.lx, im.ly, im.lz,
+                                          im.shifts, pj.x, pj.y, pj.z, tabrow + __float_as_int(pj.w));
+    h.ax += f.x; h.ay += f.y; h.az += f.z;
 }
 
 // Distance test + interaction of one neighbour.
@@ -206,7 +287,8 @@ __device__ __noinline__ float3 band_pair_clusters(const Geometry& g, float xi, f
 //  candidate and masked: 23 issue slots per candidate instead of ~33, no divergence.
 //  BOIDS = true: the per-type sums make the accepted path long; it stays behind a branch.
 template <bool BOIDS, bool LOWFIX>
-__device__ __forceinline__ void pair(Home& h, unsigned tabrow_s, const PairParam* __restrict__ tabrow,
+__device__ __forceinline__ void pair(Home& h, ParamCache& pc, RowAddr tabrow_s,
+                                     const PairParam* __restrict__ tabrow,
                                      float* __restrict__ boid_acc, const ForceArgs& a,
                                      const Geometry& g, const Image& im, int j, const float4 pj)
 {
@@ -215,24 +297,8 @@ __device__ __forceinline__ void pair(Home& h, unsigned tabrow_s, const PairParam
     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     const bool in = d2 < g.r2_hi && d2 > 1e-10f;
     if (!BOIDS) {
-        const bool band = in && d2 > g.r2_lo;
-        const unsigned qaddr = tabrow_s + (unsigned)__float_as_int(pj.w) * (unsigned)sizeof(PairParam);
-        const float4 qa = lds4(qaddr);
-        const float2 qb = lds2(qaddr + 16);
-        const float inv = fast_rsqrt(d2);  // inf for the self pair: masked below
-        const float dist = d2 * inv;
-        const float f_in = fmaf(-qa.y, dist, qa.z);
-        const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-        float s = (dist < qa.x ? f_in : f_tri) * inv;
-        s = (in && !band) ? s : 0.0f;
-        h.ax = fmaf(-s, dx, h.ax);
-        h.ay = fmaf(-s, dy, h.ay);
-        h.az = fmaf(-s, dz, h.az);
-        if (band) {
-            const float3 f = band_pair_clusters(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts, dx, dy,
-                                                dz, d2, qa, qb);
-            h.ax += f.x; h.ay += f.y; h.az += f.z;
-        }
+        // (tail of a run; the unrolled body of run_pairs calls pair_clusters directly)
+        if (needs_repair(g, pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, pj))) repair(h, tabrow, g, im, pj);
     } else if (in) {
         bool ok = true;
         if (d2 > g.r2_lo) {
@@ -250,7 +316,7 @@ __device__ __forceinline__ void pair(Home& h, unsigned tabrow_s, const PairParam
 // Four independent 16-byte loads are issued before the four tests that consume them, so
 // the L1 latency of a neighbour is hidden behind the arithmetic of the previous ones.
 template <bool BOIDS, bool LOWFIX>
-__device__ __forceinline__ void run_pairs(Home& h, unsigned tabrow_s,
+__device__ __forceinline__ void run_pairs(Home& h, ParamCache& pc, RowAddr tabrow_s,
                                           const PairParam* __restrict__ tabrow,
                                           float* __restrict__ boid_acc, const ForceArgs& a,
                                           const Geometry& g, const Image& im, int s, int e)
@@ -259,31 +325,76 @@ __device__ __forceinline__ void run_pairs(Home& h, unsigned tabrow_s,
     const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
     h.ax = h.ay = h.az = 0.0f;
     int j = s;
-    for (; j + 4 <= e; j += 4) {
-        const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
-                     p3 = ldg4(a.posw + j + 3);
-        pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j, p0);
-        pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 1, p1);
-        pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 2, p2);
-        pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 3, p3);
+    if (!BOIDS) {
+        // Software pipeline: the four 16-byte loads of group g+1 are in flight while group g
+        // is evaluated.  Most neighbour lines are first touched by this warp and come from
+        // L2 (~300 cycles); one group of arithmetic (~100 issue slots shared with the other
+        // warps of the scheduler) covers that.
+        const float4* __restrict__ src = a.posw;
+        int groups = (e - s) >> 2;
+        if (groups > 0) {
+            float4 p0 = ldg4(src + j), p1 = ldg4(src + j + 1), p2 = ldg4(src + j + 2), p3 = ldg4(src + j + 3);
+            while (true) {
+                const bool more = --groups > 0;
+                float4 n0 = p0, n1 = p1, n2 = p2, n3 = p3;
+#if GOF_FORCE_PREFETCH
+                if (more) {
+                    n0 = ldg4(src + j + 4); n1 = ldg4(src + j + 5);
+                    n2 = ldg4(src + j + 6); n3 = ldg4(src + j + 7);
+                }
+#endif
+                // four independent, branch-free evaluations the scheduler can interleave; the rare
+                // pairs in the guard band (~1 in 1e5) or below 1e-10 (the self pair) are repaired
+                // after the group, found with one vote over the four squared distances
+                const float d0 = pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, p0);
+                const float d1 = pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, p1);
+                const float d2 = pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, p2);
+                const float d3 = pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, p3);
+                const bool b0 = !(d0 < g.r2_lo) && d0 < g.r2_hi, b1 = !(d1 < g.r2_lo) && d1 < g.r2_hi,
+                           b2 = !(d2 < g.r2_lo) && d2 < g.r2_hi, b3 = !(d3 < g.r2_lo) && d3 < g.r2_hi;
+                const bool tiny = fminf(fminf(d0, d1), fminf(d2, d3)) <= 1e-10f;
+                if (b0 | b1 | b2 | b3 | tiny) {
+                    if (needs_repair(g, d0)) repair(h, tabrow, g, im, p0);
+                    if (needs_repair(g, d1)) repair(h, tabrow, g, im, p1);
+                    if (needs_repair(g, d2)) repair(h, tabrow, g, im, p2);
+                    if (needs_repair(g, d3)) repair(h, tabrow, g, im, p3);
+                }
+                j += 4;
+                if (!more) break;
+#if GOF_FORCE_PREFETCH
+                p0 = n0; p1 = n1; p2 = n2; p3 = n3;
+#else
+                p0 = ldg4(src + j); p1 = ldg4(src + j + 1); p2 = ldg4(src + j + 2); p3 = ldg4(src + j + 3);
+#endif
+            }
+        }
+    } else {
+        for (; j + 4 <= e; j += 4) {
+            const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
+                         p3 = ldg4(a.posw + j + 3);
+            pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j, p0);
+            pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j + 1, p1);
+            pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j + 2, p2);
+            pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j + 3, p3);
+        }
     }
-    for (; j < e; ++j) pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j, ldg4(a.posw + j));
+    for (; j < e; ++j) pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j, ldg4(a.posw + j));
     h.ax += ax0; h.ay += ay0; h.az += az0;
 }
 
 // Warp-uniform choice of the LOWFIX variant: callers are convergent (every lane walks the
 // same sequence of runs, possibly empty), so the vote is safe and costs no divergence.
 template <bool BOIDS>
-__device__ __forceinline__ void run_image(Home& h, unsigned tabrow_s,
+__device__ __forceinline__ void run_image(Home& h, ParamCache& pc, RowAddr tabrow_s,
                                           const PairParam* __restrict__ tabrow,
                                           float* __restrict__ boid_acc, const ForceArgs& a,
                                           const Geometry& g, int sx, int sy, int sz, int s, int e)
 {
     const Image im = make_image(h, g, sx, sy, sz);
     if (__any_sync(0xffffffffu, im.up && e > s))
-        run_pairs<BOIDS, true>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
+        run_pairs<BOIDS, true>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
     else
-        run_pairs<BOIDS, false>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
+        run_pairs<BOIDS, false>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
 }
 
 // The reference's z wrap (acceleration_updater.py:325-328) tests pos_y[i] where it
@@ -345,14 +456,26 @@ __device__ __noinline__ void run_pairs_zquirk(Home& h, const PairParam* __restri
 }
 
 template <bool BOIDS, int MODE>
-__global__ void __launch_bounds__(kForceThreads, 5)
+#ifndef GOF_FORCE_MINBLOCKS
+#define GOF_FORCE_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(kForceThreads, GOF_FORCE_MINBLOCKS)
 k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
 {
     extern __shared__ float4 smem_raw[];
     PairParam* tab = reinterpret_cast<PairParam*>(smem_raw);
     const int T = a.T;
-    float* boid_acc = reinterpret_cast<float*>(tab + T * T) + threadIdx.x;
-    for (int q = threadIdx.x; q < T * T; q += blockDim.x) tab[q] = a.table[q];
+    const int TA = T | 1;  // odd row stride of the split arrays
+    float4* tabA = reinterpret_cast<float4*>(tab + T * T);
+    float2* tabB = reinterpret_cast<float2*>(tabA + T * TA);
+    float* boid_acc = reinterpret_cast<float*>(tabB + T * TA + (T * TA & 1)) + threadIdx.x;
+    for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
+        const PairParam pp = a.table[q];
+        tab[q] = pp;
+        const int r = q / T, c = q - r * T;
+        tabA[r * TA + c] = pp.a;
+        tabB[r * TA + c] = make_float2(pp.b.x, pp.b.y);
+    }
     if (BOIDS) {
         for (int q = 0; q < T * kBoidSlots; ++q) boid_acc[q * kForceThreads] = 0.0f;
     }
@@ -371,7 +494,13 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     h.type = __float_as_int(pi.w);
     h.kinds = BOIDS ? a.kind_rows[h.type] : 0u;
     const PairParam* tabrow = tab + h.type * T;
-    const unsigned tabrow_s = (unsigned)__cvta_generic_to_shared(tabrow);
+    RowAddr tabrow_s;
+    tabrow_s.a = (unsigned)__cvta_generic_to_shared(tabA + h.type * TA);
+    tabrow_s.b = (unsigned)__cvta_generic_to_shared(tabB + h.type * TA);
+    ParamCache pc;
+    pc.t = -1;
+    pc.qa = make_float4(0.f, 0.f, 0.f, 0.f);
+    pc.qb = make_float2(0.f, 0.f);
 
     const int c = a.cell_sorted[k];
     const int cx = c % g.nbx;
@@ -405,14 +534,14 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 int s = a.start[rb + lo];
                 int e = a.start[rb + hi] + a.count[rb + hi];
                 if (!valid) e = s;
-                run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, 0, sy, sz, s, e);
+                run_image<BOIDS>(h, pc, tabrow_s, tabrow, boid_acc, a, g, 0, sy, sz, s, e);
                 // the cell across the periodic x boundary (an empty run for interior home cells:
                 // every lane makes the same calls, so the warp votes inside stay convergent)
                 const bool xedge = cx == 0 || cx == g.nbx - 1;
                 const int wc = cx == 0 ? g.nbx - 1 : 0;
                 s = a.start[rb + wc];
                 e = (valid && xedge) ? s + a.count[rb + wc] : s;
-                run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e);
+                run_image<BOIDS>(h, pc, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e);
             }
         }
     } else {
