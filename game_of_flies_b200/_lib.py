@@ -16,6 +16,7 @@ GOF_ABI_VERSION = 1
 WRAP_REFERENCE = 0
 WRAP_MINIMAGE = 1
 MAX_TYPES = 16
+KERNEL_SCALAR, KERNEL_PACKED = 0, 1
 
 E_INVALID, E_STATE, E_NOMEM, E_GRID = -1, -2, -3, -4
 
@@ -70,6 +71,7 @@ SIGNATURES = {
     "gof_engine_download": (_i, [_vp] + [_vp] * 9 + [_vp]),
     "gof_engine_snapshot": (_i, [_vp, _vp, _vp]),
     "gof_engine_read_bins": (_i, [_vp] + [_vp] * 4 + [_vp]),
+    "gof_engine_set_kernel": (_i, [_vp, _i]),
     "gof_engine_timing": (_i, [_vp, _i]),
     "gof_engine_force_time": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
     "gof_engine_last_timestep": (_i, [_vp, C.POINTER(_f), _vp]),

@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../include/gof_b200.h"
-#include "gof_force.cuh"
+#include "gof_force2.cuh"
 
 using namespace gof;
 
@@ -289,17 +289,37 @@ static int launch_force(const Geometry& g, const ForceArgs& a, bool boids, int m
     return boids ? launch_force_t<true, kModeScatter>(g, a, st) : launch_force_t<false, kModeScatter>(g, a, st);
 }
 
-// exclusive scan of m ints; tile_sums needs cdiv(m, kScanTile) ints
+// exclusive scan of m ints (PAD2: of the counts rounded up to even); tile_sums needs
+// cdiv(m, kScanTile) ints
+template <bool PAD2>
 static int launch_scan(const int* in, int m, int* tile_sums, int* out, cudaStream_t st)
 {
     const int tiles = cdiv(m, kScanTile);
     if (tiles <= 1) {
-        GOF_LAUNCH(k_scan_apply, 1, kScanThreads, 0, st, in, m, (const int*)nullptr, out);
+        GOF_LAUNCH(k_scan_apply<PAD2>, 1, kScanThreads, 0, st, in, m, (const int*)nullptr, out);
         return 0;
     }
-    GOF_LAUNCH(k_scan_tile_sums, tiles, kScanThreads, 0, st, in, m, tile_sums);
+    GOF_LAUNCH(k_scan_tile_sums<PAD2>, tiles, kScanThreads, 0, st, in, m, tile_sums);
     GOF_LAUNCH(k_scan_tile_prefix, 1, kScanThreads, 0, st, tile_sums, tiles);
-    GOF_LAUNCH(k_scan_apply, tiles, kScanThreads, 0, st, in, m, (const int*)tile_sums, out);
+    GOF_LAUNCH(k_scan_apply<PAD2>, tiles, kScanThreads, 0, st, in, m, (const int*)tile_sums, out);
+    return 0;
+}
+
+static size_t force2_smem_bytes(int T)
+{
+    return (size_t)T * T * (sizeof(PairParam) + sizeof(float4) + sizeof(float)) + 16;
+}
+
+// the packed two-homes-per-lane Clusters kernel; `slots` = upper bound of padded slots
+static int launch_force2(const Geometry& g, const ForceArgs& a, int slots, cudaStream_t st)
+{
+    if (slots <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GOF_CUDA(cudaFuncSetAttribute(k_force2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    GOF_LAUNCH(k_force2, cdiv(cdiv(slots, 2), kForce2Threads), kForce2Threads, force2_smem_bytes(a.T), st, g, a);
     return 0;
 }
 
@@ -429,16 +449,21 @@ k_snapshot(const float4* __restrict__ posw, const float4* __restrict__ veli, int
     xyz[3 * (size_t)id + 2] = p.z;
 }
 
-// bins of the last step in the reference's layout
+// bins of the last step in the reference's layout; the snapshot may sit on padded segments
 __global__ void __launch_bounds__(kEwThreads)
-k_export_bins(const float4* __restrict__ veli_sorted, const int* __restrict__ cell_sorted, int n,
-              int* __restrict__ particle_bins, int* __restrict__ particle_indices)
+k_export_bins(const float4* __restrict__ veli_sorted, const int* __restrict__ cell_sorted,
+              const int* __restrict__ start, const int* __restrict__ pstart,
+              const int* __restrict__ count, int num_cells, int* __restrict__ particle_bins,
+              int* __restrict__ particle_indices)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    if (k >= pstart[num_cells]) return;
+    const int c = cell_sorted[k];
+    const int r = k - pstart[c];
+    if (r >= count[c]) return;  // padding slot
     const int id = __float_as_int(veli_sorted[k].w);
-    if (particle_bins) particle_bins[id] = cell_sorted[k];
-    if (particle_indices) particle_indices[k] = id;
+    if (particle_bins) particle_bins[id] = c;
+    if (particle_indices) particle_indices[start[c] + r] = id;
 }
 
 // reference-layout inputs -> cell-sorted float4 scratch for gof_accelerator
@@ -516,10 +541,10 @@ extern "C" int gof_setup_bins(const float* d_pos_x, const float* d_pos_y, const 
                    (const float4*)nullptr, (const float4*)nullptr, d_pos_x, d_pos_y, d_pos_z, n, g,
                    d_particle_bins, d_bin_offsets, d_counts, none);
     }
-    if (int rc = launch_scan(d_counts, num_bins, tile_sums, d_starts, st)) return rc;
+    if (int rc = launch_scan<false>(d_counts, num_bins, tile_sums, d_starts, st)) return rc;
     if (n > 0) {
         GOF_LAUNCH(k_scatter_ids<true>, cdiv(n, kBinThreads), kBinThreads, 0, st, (const float4*)nullptr, n,
-                   d_particle_bins, d_bin_offsets, d_starts, slot_id, d_particle_indices /* scratch: rewritten below */);
+                   d_particle_bins, d_bin_offsets, d_starts, slot_id);
         GOF_LAUNCH(k_rank_indices, cdiv(n, kBinThreads), kBinThreads, 0, st, n, d_particle_bins, d_starts,
                    d_counts, slot_id, d_bin_offsets, d_particle_indices);
     }
@@ -579,6 +604,7 @@ extern "C" int gof_accelerator(const float* d_pos_x, const float* d_pos_y, const
     a.veli = veli;
     a.cell_sorted = cell_sorted;
     a.start = d_bin_starts;
+    a.pstart = d_bin_starts;
     a.count = d_bin_counts;
     a.home_begin = 0;
     a.home_count = n;
@@ -659,14 +685,17 @@ struct gof_engine {
     Geometry geom{};
     HostSpecies species;
     bool species_dirty = true;
-    bool bound = false, uploaded = false, binned = false;
+    bool bound = false, uploaded = false, binned = false, binned_packed = false;
+    bool want_packed = false;  // gof_engine_set_kernel
     int parity = 0;  // which max_sq_speed slot describes the resident velocities
 
     // carved from the arena
     size_t arena_bytes = 0;
     float4 *posw[2] = {nullptr, nullptr}, *veli[2] = {nullptr, nullptr}, *acc = nullptr;
     int *cell_of = nullptr, *off = nullptr, *slot_id = nullptr, *slot_src = nullptr, *cell_sorted = nullptr;
-    int *count = nullptr, *start = nullptr, *tile_sums = nullptr;
+    int *count = nullptr, *start = nullptr, *pstart = nullptr, *tile_sums = nullptr;
+    float4 *dup_a = nullptr, *dup_b = nullptr;  // duplicated snapshot of the packed kernel
+    int slot_capacity = 0;                      // capacity + num_cells + 2 (even-padded segments)
     StepScalars* scalars = nullptr;
     DeviceSpecies dspecies{};
     float* stage[9] = {};  // SoA staging: pos xyz, vel xyz, acc xyz
@@ -694,18 +723,24 @@ static size_t engine_layout(gof_engine* e, char* base)
     };
     const size_t cap = (size_t)e->capacity;
     const size_t cells = (size_t)e->geom.num_cells + 2;
-    for (int b = 0; b < 2; ++b) {
-        e->posw[b] = (float4*)take(cap * sizeof(float4));
-        e->veli[b] = (float4*)take(cap * sizeof(float4));
-    }
+    const size_t slots = cap + cells;  // padded snapshot: at most one extra slot per cell
+    e->slot_capacity = (int)slots;
+    // [0] = rest state (compact, last step's cell order), [1] = this step's snapshot (padded slots)
+    e->posw[0] = (float4*)take(cap * sizeof(float4));
+    e->veli[0] = (float4*)take(cap * sizeof(float4));
+    e->posw[1] = (float4*)take(slots * sizeof(float4));
+    e->veli[1] = (float4*)take(slots * sizeof(float4));
+    e->dup_a = (float4*)take(slots * sizeof(float4));
+    e->dup_b = (float4*)take(slots * sizeof(float4));
     e->acc = (float4*)take(cap * sizeof(float4));
     e->cell_of = (int*)take(cap * sizeof(int));
     e->off = (int*)take(cap * sizeof(int));
-    e->slot_id = (int*)take(cap * sizeof(int));
-    e->slot_src = (int*)take(cap * sizeof(int));
-    e->cell_sorted = (int*)take(cap * sizeof(int));
+    e->slot_id = (int*)take(slots * sizeof(int));
+    e->slot_src = (int*)take(16);
+    e->cell_sorted = (int*)take(slots * sizeof(int));
     e->count = (int*)take(cells * sizeof(int));
     e->start = (int*)take(cells * sizeof(int));
+    e->pstart = (int*)take(cells * sizeof(int));
     e->tile_sums = (int*)take((size_t)(cdiv((int)cells, kScanTile) + 1) * sizeof(int));
     e->scalars = (StepScalars*)take(sizeof(StepScalars));
     char* sp = take(species_bytes(e->T));
@@ -744,6 +779,16 @@ extern "C" void gof_engine_destroy(gof_engine* e)
     if (!e) return;
     for (cudaEvent_t v : e->ev) cudaEventDestroy(v);
     delete e;
+}
+
+extern "C" int gof_engine_set_kernel(gof_engine* e, int kernel)
+{
+    if (!e) return fail(GOF_E_INVALID, "null engine");
+    if (kernel != GOF_KERNEL_SCALAR && kernel != GOF_KERNEL_PACKED)
+        return fail(GOF_E_INVALID, "gof_engine_set_kernel: unknown kernel");
+    e->want_packed = kernel == GOF_KERNEL_PACKED;
+    e->binned = false;
+    return 0;
 }
 
 extern "C" int gof_engine_timing(gof_engine* e, int enable)
@@ -836,25 +881,44 @@ extern "C" int gof_engine_upload(gof_engine* e, const float* px, const float* py
     return 0;
 }
 
+// Which force kernel a step uses: the packed two-homes kernel needs every species pair to be
+// of the Clusters kind (its profile is evaluated branch-free for both homes at once).
+static bool engine_packed(const gof_engine* e) { return e->want_packed && !e->species.has_boids; }
+
 // setup_bins on the resident state: posw[0]/veli[0]/acc (rest order) -> posw[1]/veli[1]
-// (cell order, velocities kicked by step1 when `kick`), cell tables filled.
+// (cell order, velocities kicked by step1 when `kick`), cell tables filled.  For the packed
+// kernel the snapshot is laid out on even-padded cell segments and written a second time in
+// the duplicated layout.
 static int engine_bin(gof_engine* e, bool kick, cudaStream_t st)
 {
     const Geometry& g = e->geom;
     const int n = e->n;
+    const bool packed = engine_packed(e);
     GOF_CUDA(cudaMemsetAsync(e->count, 0, (size_t)(g.num_cells + 2) * sizeof(int), st));
     MigrateOut none{};
     GOF_LAUNCH(k_hash_count<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->posw[0], e->veli[0], e->acc,
                (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, n, g, e->cell_of, e->off,
                e->count, none);
-    if (int rc = launch_scan(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
+    if (int rc = launch_scan<false>(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
+    if (packed)
+        if (int rc = launch_scan<true>(e->count, g.num_cells + 1, e->tile_sums, e->pstart, st)) return rc;
+    const int* layout = packed ? e->pstart : e->start;
     GOF_LAUNCH(k_scatter_ids<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->veli[0], n, e->cell_of, e->off,
-               e->start, e->slot_id, e->slot_src);
-    GOF_LAUNCH(k_rank_gather_kick, cdiv(n, kBinThreads), kBinThreads, 0, st, n, e->cell_of, e->start, e->count,
-               e->slot_id, e->slot_src, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1],
-               e->cell_sorted, e->scalars, kick ? 1 : 0);
+               layout, e->slot_id);
+    GOF_LAUNCH(k_rank_gather_kick, cdiv(n, kBinThreads), kBinThreads, 0, st, n, e->cell_of, layout, e->count,
+               e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1], e->cell_sorted,
+               packed ? e->dup_a : (float4*)nullptr, packed ? e->dup_b : (float4*)nullptr, e->scalars,
+               kick ? 1 : 0);
     e->binned = true;
+    e->binned_packed = packed;
     return 0;
+}
+
+// force (+ integrate) on the snapshot engine_bin just built
+static int engine_force(gof_engine* e, const ForceArgs& a, cudaStream_t st)
+{
+    if (engine_packed(e)) return launch_force2(e->geom, a, e->n + e->geom.num_cells, st);
+    return launch_force(e->geom, a, true, kModeIntegrate, st);
 }
 
 static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
@@ -864,6 +928,9 @@ static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
     a->veli = e->veli[1];
     a->cell_sorted = e->cell_sorted;
     a->start = e->start;
+    a->pstart = engine_packed(e) ? e->pstart : e->start;
+    a->dup_a = e->dup_a;
+    a->dup_b = e->dup_b;
     a->count = e->count;
     a->home_begin = 0;
     a->home_count = e->n;
@@ -903,7 +970,7 @@ extern "C" int gof_engine_step(gof_engine* e, int n_steps, float timestep, int w
             }
             GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used], st));
         }
-        if (int rc = launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st)) return rc;
+        if (int rc = engine_force(e, a, st)) return rc;
         if (timed) {
             GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used + 1], st));
             ++e->ev_used;
@@ -924,7 +991,7 @@ extern "C" int gof_engine_accelerate(gof_engine* e, int wrap_mode, void* stream)
     engine_force_args(e, wrap_mode, &a);
     a.integrate = 0;
     a.parity_out = e->parity;  // velocities unchanged: the maximum is re-accumulated into the same slot
-    return launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st);
+    return engine_force(e, a, st);
 }
 
 extern "C" int gof_engine_download(gof_engine* e, float* px, float* py, float* pz, float* vx, float* vy,
@@ -962,8 +1029,9 @@ extern "C" int gof_engine_read_bins(gof_engine* e, int32_t* particle_bins, int32
     cudaStream_t st = (cudaStream_t)stream;
     const int n = e->n;
     // posw[1]/veli[1] still hold the cell-ordered snapshot the last force kernel read
-    GOF_LAUNCH(k_export_bins, cdiv(n, kEwThreads), kEwThreads, 0, st, e->veli[1], e->cell_sorted, n,
-               e->stage_bins, e->stage_indices);
+    GOF_LAUNCH(k_export_bins, cdiv(e->slot_capacity, kEwThreads), kEwThreads, 0, st, e->veli[1], e->cell_sorted,
+               e->start, e->binned_packed ? e->pstart : e->start, e->count, e->geom.num_cells, e->stage_bins,
+               e->stage_indices);
     if (particle_bins) GOF_CUDA(cudaMemcpyAsync(particle_bins, e->stage_bins, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
     if (particle_indices) GOF_CUDA(cudaMemcpyAsync(particle_indices, e->stage_indices, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
     const size_t cb = (size_t)e->geom.num_cells * sizeof(int);

@@ -142,7 +142,14 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total)
     return warp_prefix + inc - v;
 }
 
+// PAD2 = true scans the counts rounded up to even numbers: the padded cell starts of the
+// two-homes-per-lane force kernel (every cell segment gets an even number of slots so
+// that the two particles of a lane always share a cell).
+template <bool PAD2>
+__device__ __forceinline__ int scan_value(int v) { return PAD2 ? ((v + 1) & ~1) : v; }
+
 // Phase 1: sum of every tile of kScanTile counts.
+template <bool PAD2>
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_tile_sums(const int* __restrict__ in, int m, int* __restrict__ tile_sums)
 {
@@ -150,7 +157,7 @@ k_scan_tile_sums(const int* __restrict__ in, int m, int* __restrict__ tile_sums)
     int s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
-        if (base + k < m) s += in[base + k];
+        if (base + k < m) s += scan_value<PAD2>(in[base + k]);
     int total;
     block_exclusive_scan(s, total);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
@@ -174,6 +181,7 @@ k_scan_tile_prefix(int* __restrict__ tile_sums, int tiles)
 // Phase 3: scan inside each tile and add the tile prefix.  With a single tile
 // (up to 4096 cells: every configuration the reference UI can build) phases 1
 // and 2 are skipped and this is the whole scan.
+template <bool PAD2>
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_prefix,
              int* __restrict__ out)
@@ -183,7 +191,7 @@ k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_pre
     int s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        v[k] = (base + k < m) ? in[base + k] : 0;
+        v[k] = (base + k < m) ? scan_value<PAD2>(in[base + k]) : 0;
         s += v[k];
     }
     int total;
@@ -195,18 +203,16 @@ k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_pre
     }
 }
 
-// Arrival-order scatter of (id, source index) into the cell segments.
+// Arrival-order scatter of the ids into the cell segments (`start` may be the padded table).
 template <bool SOA>
 __global__ void __launch_bounds__(kBinThreads)
 k_scatter_ids(const float4* __restrict__ veli, int n, const int* __restrict__ cell_of,
               const int* __restrict__ off, const int* __restrict__ start,
-              int* __restrict__ slot_id, int* __restrict__ slot_src)
+              int* __restrict__ slot_id)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int s = start[cell_of[i]] + off[i];
-    slot_id[s] = SOA ? i : __float_as_int(veli[i].w);
-    slot_src[s] = i;
+    slot_id[start[cell_of[i]] + off[i]] = SOA ? i : __float_as_int(veli[i].w);
 }
 
 // Rank pass for the reference-layout API: final position of every particle in its
@@ -216,9 +222,8 @@ k_rank_indices(int n, const int* __restrict__ cell_of, const int* __restrict__ s
                const int* __restrict__ count, const int* __restrict__ slot_id,
                int* __restrict__ bin_offsets, int* __restrict__ particle_indices)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const int id = slot_id[s];
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
     const int c = cell_of[id];
     const int b = start[c], e = b + count[c];
     int rank = 0;
@@ -241,29 +246,37 @@ struct StepScalars {
     int error;                      // sticky device-side error flags
 };
 
+constexpr float kDummyPos = 1e18f;  // a padding slot sits here: (1e18)^2 * 3 still fits fp32, never in range
+
+// One thread per SOURCE particle (rest order): its rank among the ids of its cell is its
+// slot in the cell's segment.  `pstart` is the table the segments are laid out with: the
+// true starts, or the even-padded starts when `dup_a` is given.  In padded mode the last
+// particle of an odd cell also writes the dummy that fills the segment, and every particle
+// is written a second time in the duplicated layout {x, x, y, y} {z, z, type, 0} that the
+// packed (two homes per lane) force kernel streams.
 __global__ void __launch_bounds__(kBinThreads)
-k_rank_gather_kick(int n, const int* __restrict__ cell_of, const int* __restrict__ start,
+k_rank_gather_kick(int n, const int* __restrict__ cell_of, const int* __restrict__ pstart,
                    const int* __restrict__ count, const int* __restrict__ slot_id,
-                   const int* __restrict__ slot_src, int sentinel_cell,
-                   const float4* __restrict__ posw_in, const float4* __restrict__ veli_in,
-                   const float4* __restrict__ acc_in, float4* __restrict__ posw_out,
-                   float4* __restrict__ veli_out, int* __restrict__ cell_sorted,
-                   const StepScalars* __restrict__ scalars, int apply_kick)
+                   int sentinel_cell, const float4* __restrict__ posw_in,
+                   const float4* __restrict__ veli_in, const float4* __restrict__ acc_in,
+                   float4* __restrict__ posw_out, float4* __restrict__ veli_out,
+                   int* __restrict__ cell_sorted, float4* __restrict__ dup_a,
+                   float4* __restrict__ dup_b, const StepScalars* __restrict__ scalars,
+                   int apply_kick)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const int src = slot_src[s];
-    const int c = cell_of[src];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell_of[i];
     if (c == sentinel_cell) return;  // dead slot: dropped by the sort
-    const int id = slot_id[s];
-    const int b = start[c], e = b + count[c];
+    float4 v = veli_in[i];
+    const int id = __float_as_int(v.w);
+    const int b = pstart[c], cnt = count[c], e = b + cnt;
     int rank = 0;
     for (int t = b; t < e; ++t) rank += (slot_id[t] < id);
     const int dst = b + rank;
 
-    float4 v = veli_in[src];
     if (apply_kick) {
-        const float4 a = acc_in[src];
+        const float4 a = acc_in[i];
         const float h = 0.5f * scalars->dt;
         v.x = fmaf(a.x, h, v.x);
         v.y = fmaf(a.y, h, v.y);
@@ -274,9 +287,22 @@ k_rank_gather_kick(int n, const int* __restrict__ cell_of, const int* __restrict
             v.x *= k; v.y *= k; v.z *= k;
         }
     }
-    posw_out[dst] = posw_in[src];
+    const float4 p = posw_in[i];
+    posw_out[dst] = p;
     veli_out[dst] = v;
     cell_sorted[dst] = c;
+    if (dup_a) {
+        dup_a[dst] = make_float4(p.x, p.x, p.y, p.y);
+        dup_b[dst] = make_float4(p.z, p.z, p.w, 0.0f);
+        if (rank == cnt - 1 && (cnt & 1)) {
+            const float D = kDummyPos;
+            posw_out[dst + 1] = make_float4(D, D, D, __int_as_float(0));
+            veli_out[dst + 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            cell_sorted[dst + 1] = c;
+            dup_a[dst + 1] = make_float4(D, D, D, D);
+            dup_b[dst + 1] = make_float4(D, D, __int_as_float(0), 0.0f);
+        }
+    }
 }
 
 }  // namespace gof

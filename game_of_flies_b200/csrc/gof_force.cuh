@@ -17,10 +17,6 @@
 #pragma once
 #include "gof_binning.cuh"
 
-#ifndef GOF_FORCE_PREFETCH
-#define GOF_FORCE_PREFETCH 1
-#endif
-
 namespace gof {
 
 constexpr int kForceThreads = 128;
@@ -35,8 +31,12 @@ struct ForceArgs {
     const float4* posw;       // {x, y, z, type bits}, cell order (owned + appended halo)
     const float4* veli;       // {vx, vy, vz, id bits}, cell order, already kicked by step1
     const int* cell_sorted;   // cell of every home particle
-    const int* start;         // first index of every cell
+    const int* start;         // first index of every cell in the compact (rest) order
     const int* count;         // population of every cell
+    const int* pstart;        // first slot of every cell in the snapshot the kernel reads
+                              // (== start, or the even-padded table of the packed kernel)
+    const float4* dup_a;      // packed kernel only: {x, x, y, y} per snapshot slot
+    const float4* dup_b;      //                     {z, z, type bits, 0}
     int home_begin, home_count;
     const PairParam* table;   // [T*T]
     const unsigned* kind_rows;  // [T] bit j of row i set => (i, j) is of Boids kind
@@ -223,36 +223,18 @@ __device__ __noinline__ float3 repair_pair_clusters(const Geometry& g, float xi,
     return make_float3(-s * dx, -s * dy, -s * dz);
 }
 
-// The species-pair parameters of the neighbour type seen last, kept in registers.
-// Particles are ordered by id inside a cell and the reference numbers its particles
-// species by species (state_parameters.py:76-81), so a run of neighbours changes type
-// only a few times: the two shared-memory loads below are predicated off for ~85% of the
-// pairs.  That matters because the SM returns at most 128 B/clk from L1/shared to the
-// register file: 16 B of neighbour + 24 B of parameters per lane and pair made that path,
-// not the issue slots, the limiter.
-struct ParamCache {
-    int t;
-    float4 qa;
-    float2 qb;
-};
-
 // Branch-free Clusters pair (see `pair` below).  Adds the force iff d2 < r2_lo and
 // returns d2 so that the caller can spot the rare pairs that need the cold path.
 template <bool LOWFIX>
-__device__ __forceinline__ float pair_clusters(Home& h, ParamCache& pc, RowAddr tabrow_s,
-                                               const Geometry& g, const Image& im, const float4 pj)
+__device__ __forceinline__ float pair_clusters(Home& h, RowAddr tabrow_s, const Geometry& g,
+                                               const Image& im, const float4 pj)
 {
     float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
     if (LOWFIX) { dx += im.lx; dy += im.ly; dz += im.lz; }
     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const int tj = __float_as_int(pj.w);
-    if (tj != pc.t) {
-        pc.t = tj;
-        pc.qa = lds4(tabrow_s.a + (unsigned)tj * 16u);
-        pc.qb = lds2(tabrow_s.b + (unsigned)tj * 8u);
-    }
-    const float4 qa = pc.qa;
-    const float2 qb = pc.qb;
+    const unsigned tj = (unsigned)__float_as_int(pj.w);
+    const float4 qa = lds4(tabrow_s.a + tj * 16u);
+    const float2 qb = lds2(tabrow_s.b + tj * 8u);
     const float inv = fast_rsqrt(d2 + kTinyD2);
     const float dist = d2 * inv;
     const float f_in = fmaf(-qa.y, dist, qa.z);
@@ -287,8 +269,7 @@ __device__ __forceinline__ void repair(Home& h, const PairParam* __restrict__ ta
 //  candidate and masked: 23 issue slots per candidate instead of ~33, no divergence.
 //  BOIDS = true: the per-type sums make the accepted path long; it stays behind a branch.
 template <bool BOIDS, bool LOWFIX>
-__device__ __forceinline__ void pair(Home& h, ParamCache& pc, RowAddr tabrow_s,
-                                     const PairParam* __restrict__ tabrow,
+__device__ __forceinline__ void pair(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
                                      float* __restrict__ boid_acc, const ForceArgs& a,
                                      const Geometry& g, const Image& im, int j, const float4 pj)
 {
@@ -298,7 +279,7 @@ __device__ __forceinline__ void pair(Home& h, ParamCache& pc, RowAddr tabrow_s,
     const bool in = d2 < g.r2_hi && d2 > 1e-10f;
     if (!BOIDS) {
         // (tail of a run; the unrolled body of run_pairs calls pair_clusters directly)
-        if (needs_repair(g, pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, pj))) repair(h, tabrow, g, im, pj);
+        if (needs_repair(g, pair_clusters<LOWFIX>(h, tabrow_s, g, im, pj))) repair(h, tabrow, g, im, pj);
     } else if (in) {
         bool ok = true;
         if (d2 > g.r2_lo) {
@@ -316,7 +297,7 @@ __device__ __forceinline__ void pair(Home& h, ParamCache& pc, RowAddr tabrow_s,
 // Four independent 16-byte loads are issued before the four tests that consume them, so
 // the L1 latency of a neighbour is hidden behind the arithmetic of the previous ones.
 template <bool BOIDS, bool LOWFIX>
-__device__ __forceinline__ void run_pairs(Home& h, ParamCache& pc, RowAddr tabrow_s,
+__device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
                                           const PairParam* __restrict__ tabrow,
                                           float* __restrict__ boid_acc, const ForceArgs& a,
                                           const Geometry& g, const Image& im, int s, int e)
@@ -325,76 +306,51 @@ __device__ __forceinline__ void run_pairs(Home& h, ParamCache& pc, RowAddr tabro
     const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
     h.ax = h.ay = h.az = 0.0f;
     int j = s;
-    if (!BOIDS) {
-        // Software pipeline: the four 16-byte loads of group g+1 are in flight while group g
-        // is evaluated.  Most neighbour lines are first touched by this warp and come from
-        // L2 (~300 cycles); one group of arithmetic (~100 issue slots shared with the other
-        // warps of the scheduler) covers that.
-        const float4* __restrict__ src = a.posw;
-        int groups = (e - s) >> 2;
-        if (groups > 0) {
-            float4 p0 = ldg4(src + j), p1 = ldg4(src + j + 1), p2 = ldg4(src + j + 2), p3 = ldg4(src + j + 3);
-            while (true) {
-                const bool more = --groups > 0;
-                float4 n0 = p0, n1 = p1, n2 = p2, n3 = p3;
-#if GOF_FORCE_PREFETCH
-                if (more) {
-                    n0 = ldg4(src + j + 4); n1 = ldg4(src + j + 5);
-                    n2 = ldg4(src + j + 6); n3 = ldg4(src + j + 7);
-                }
-#endif
-                // four independent, branch-free evaluations the scheduler can interleave; the rare
-                // pairs in the guard band (~1 in 1e5) or below 1e-10 (the self pair) are repaired
-                // after the group, found with one vote over the four squared distances
-                const float d0 = pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, p0);
-                const float d1 = pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, p1);
-                const float d2 = pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, p2);
-                const float d3 = pair_clusters<LOWFIX>(h, pc, tabrow_s, g, im, p3);
-                const bool b0 = !(d0 < g.r2_lo) && d0 < g.r2_hi, b1 = !(d1 < g.r2_lo) && d1 < g.r2_hi,
-                           b2 = !(d2 < g.r2_lo) && d2 < g.r2_hi, b3 = !(d3 < g.r2_lo) && d3 < g.r2_hi;
-                const bool tiny = fminf(fminf(d0, d1), fminf(d2, d3)) <= 1e-10f;
-                if (b0 | b1 | b2 | b3 | tiny) {
-                    if (needs_repair(g, d0)) repair(h, tabrow, g, im, p0);
-                    if (needs_repair(g, d1)) repair(h, tabrow, g, im, p1);
-                    if (needs_repair(g, d2)) repair(h, tabrow, g, im, p2);
-                    if (needs_repair(g, d3)) repair(h, tabrow, g, im, p3);
-                }
-                j += 4;
-                if (!more) break;
-#if GOF_FORCE_PREFETCH
-                p0 = n0; p1 = n1; p2 = n2; p3 = n3;
-#else
-                p0 = ldg4(src + j); p1 = ldg4(src + j + 1); p2 = ldg4(src + j + 2); p3 = ldg4(src + j + 3);
-#endif
+    for (; j + 4 <= e; j += 4) {
+        // four independent 16-byte loads issued ahead of the arithmetic that consumes them
+        const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
+                     p3 = ldg4(a.posw + j + 3);
+        if (!BOIDS) {
+            // four independent, branch-free evaluations the scheduler can interleave; the rare
+            // pairs in the guard band (~1 in 1e5) or below 1e-10 (the self pair) are repaired
+            // after the group, found with one vote over the four squared distances
+            const float d0 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p0);
+            const float d1 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p1);
+            const float d2 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p2);
+            const float d3 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p3);
+            const bool b0 = !(d0 < g.r2_lo) && d0 < g.r2_hi, b1 = !(d1 < g.r2_lo) && d1 < g.r2_hi,
+                       b2 = !(d2 < g.r2_lo) && d2 < g.r2_hi, b3 = !(d3 < g.r2_lo) && d3 < g.r2_hi;
+            const bool tiny = fminf(fminf(d0, d1), fminf(d2, d3)) <= 1e-10f;
+            if (b0 | b1 | b2 | b3 | tiny) {
+                if (needs_repair(g, d0)) repair(h, tabrow, g, im, p0);
+                if (needs_repair(g, d1)) repair(h, tabrow, g, im, p1);
+                if (needs_repair(g, d2)) repair(h, tabrow, g, im, p2);
+                if (needs_repair(g, d3)) repair(h, tabrow, g, im, p3);
             }
-        }
-    } else {
-        for (; j + 4 <= e; j += 4) {
-            const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
-                         p3 = ldg4(a.posw + j + 3);
-            pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j, p0);
-            pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j + 1, p1);
-            pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j + 2, p2);
-            pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j + 3, p3);
+        } else {
+            pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j, p0);
+            pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 1, p1);
+            pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 2, p2);
+            pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 3, p3);
         }
     }
-    for (; j < e; ++j) pair<BOIDS, LOWFIX>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, j, ldg4(a.posw + j));
+    for (; j < e; ++j) pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j, ldg4(a.posw + j));
     h.ax += ax0; h.ay += ay0; h.az += az0;
 }
 
 // Warp-uniform choice of the LOWFIX variant: callers are convergent (every lane walks the
 // same sequence of runs, possibly empty), so the vote is safe and costs no divergence.
 template <bool BOIDS>
-__device__ __forceinline__ void run_image(Home& h, ParamCache& pc, RowAddr tabrow_s,
+__device__ __forceinline__ void run_image(Home& h, RowAddr tabrow_s,
                                           const PairParam* __restrict__ tabrow,
                                           float* __restrict__ boid_acc, const ForceArgs& a,
                                           const Geometry& g, int sx, int sy, int sz, int s, int e)
 {
     const Image im = make_image(h, g, sx, sy, sz);
     if (__any_sync(0xffffffffu, im.up && e > s))
-        run_pairs<BOIDS, true>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
+        run_pairs<BOIDS, true>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
     else
-        run_pairs<BOIDS, false>(h, pc, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
+        run_pairs<BOIDS, false>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
 }
 
 // The reference's z wrap (acceleration_updater.py:325-328) tests pos_y[i] where it
@@ -497,10 +453,6 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     RowAddr tabrow_s;
     tabrow_s.a = (unsigned)__cvta_generic_to_shared(tabA + h.type * TA);
     tabrow_s.b = (unsigned)__cvta_generic_to_shared(tabB + h.type * TA);
-    ParamCache pc;
-    pc.t = -1;
-    pc.qa = make_float4(0.f, 0.f, 0.f, 0.f);
-    pc.qb = make_float2(0.f, 0.f);
 
     const int c = a.cell_sorted[k];
     const int cx = c % g.nbx;
@@ -531,17 +483,17 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 // the x-adjacent cells that need no shift are one contiguous run
                 const int lo = cx > 0 ? cx - 1 : 0;
                 const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
-                int s = a.start[rb + lo];
-                int e = a.start[rb + hi] + a.count[rb + hi];
+                int s = a.pstart[rb + lo];
+                int e = a.pstart[rb + hi] + a.count[rb + hi];
                 if (!valid) e = s;
-                run_image<BOIDS>(h, pc, tabrow_s, tabrow, boid_acc, a, g, 0, sy, sz, s, e);
+                run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, 0, sy, sz, s, e);
                 // the cell across the periodic x boundary (an empty run for interior home cells:
                 // every lane makes the same calls, so the warp votes inside stay convergent)
                 const bool xedge = cx == 0 || cx == g.nbx - 1;
                 const int wc = cx == 0 ? g.nbx - 1 : 0;
-                s = a.start[rb + wc];
+                s = a.pstart[rb + wc];
                 e = (valid && xedge) ? s + a.count[rb + wc] : s;
-                run_image<BOIDS>(h, pc, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e);
+                run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e);
             }
         }
     } else {
@@ -563,7 +515,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                     else if (nx >= g.nbx) { nx -= g.nbx; sx = -1; }
                     // half stencil of set_bin_neighbours (acceleration_updater.py:140-215)
                     const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
-                    const int s = a.start[rb + nx];
+                    const int s = a.pstart[rb + nx];
                     const int e = valid ? s + a.count[rb + nx] : s;
                     run_pairs_zquirk<BOIDS>(h, tabrow, boid_acc, a, g, s, e, sx, sy, direct);
                 }

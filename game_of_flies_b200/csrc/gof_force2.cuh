@@ -1,0 +1,371 @@
+// gof_force2.cuh -- the Clusters force kernel of the resident engine: two home particles
+// per lane, Blackwell packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2, sm_100+).
+//
+// Why this shape.  ncu on the one-home kernel (profiles/r01_force_scalar_*.txt) showed it
+// limited by two per-SM rates at once: instruction issue (~25 slots per candidate pair)
+// and the 128 B/clk return path from L1/shared to the register file (16 B of neighbour
+// + 24 B of species parameters per lane and pair).  Here a lane owns TWO consecutive
+// particles of the same cell, so that
+//   * every broadcast neighbour load (2 x 16 B, duplicated layout {x,x,y,y} {z,z,type,0})
+//     feeds two pairs: 16 B per lane and pair, and no register shuffling to form operands;
+//   * separations, squared distances, profile and accumulation are one packed instruction
+//     for both pairs: ~15 issue slots per pair;
+//   * the species parameters live in registers and are reloaded only when the neighbour
+//     type changes (particles are ordered by id inside a cell and ids are numbered species
+//     by species, so that happens ~once per 6 neighbours).
+// The cell segments are padded to an even number of slots (gof_binning.cuh) so that the
+// two particles of a lane always share a cell and therefore walk the same runs.
+//
+// Semantics are those of k_force<false, kModeIntegrate> (gof_force.cuh): same stencil,
+// same guard band / float64 repair of the cut-off, same reference z-wrap path for the
+// edge layers (taken per home particle through the scalar code), same fused integrator.
+#pragma once
+#include "gof_force.cuh"
+
+namespace gof {
+
+constexpr int kForce2Threads = 128;  // 256 particles per block
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// Packed species parameters of (home type 0, home type 1) x current neighbour type for
+//   f(d) = s1 * (hw - |d - mid|) + cc * min(d - r_min, 0),   cc = -k0 - s1
+// which equals the reference profile: the triangle for d >= r_min, f_min - k0 d below.
+struct PackedParams {
+    float2 nrmin;  // -r_min
+    float2 nmid;   // -mid
+    float2 ns1;    // -s1
+    float2 fmax;   // s1 * hw
+    float2 cc;     // -k0 - s1
+    int type;      // neighbour type these belong to
+};
+
+// derived per-pair table in shared memory: {-r_min, -mid, -s1, f_max} and cc
+struct Derived {
+    const float4* d4;
+    const float* cc;
+    int T;
+};
+
+__device__ __forceinline__ void load_params(PackedParams& p, const Derived& d, int t0, int t1, int tj)
+{
+    const float4 a = d.d4[t0 * d.T + tj], b = d.d4[t1 * d.T + tj];
+    p.nrmin = f2(a.x, b.x);
+    p.nmid = f2(a.y, b.y);
+    p.ns1 = f2(a.z, b.z);
+    p.fmax = f2(a.w, b.w);
+    p.cc = f2(d.cc[t0 * d.T + tj], d.cc[t1 * d.T + tj]);
+    p.type = tj;
+}
+
+// The two home particles of a lane as seen by one run of neighbours.
+struct Image2 {
+    float2 nx, ny, nz;     // -(home + s * L), rounded
+    float2 nlx, nly, nlz;  // -(what the rounded sum lost); only used by LOWFIX runs
+    int shifts;
+    bool up;
+};
+
+struct Home2 {
+    float2 x, y, z;
+    float2 ax, ay, az;
+    int t0, t1;
+};
+
+__device__ __forceinline__ Image2 make_image2(const Home2& h, const Geometry& g, int sx, int sy, int sz)
+{
+    Image2 im;
+    float hi, lo;
+    shifted(h.x.x, sx, g.Lx, hi, lo); im.nx.x = -hi; im.nlx.x = -lo;
+    shifted(h.x.y, sx, g.Lx, hi, lo); im.nx.y = -hi; im.nlx.y = -lo;
+    shifted(h.y.x, sy, g.Ly, hi, lo); im.ny.x = -hi; im.nly.x = -lo;
+    shifted(h.y.y, sy, g.Ly, hi, lo); im.ny.y = -hi; im.nly.y = -lo;
+    shifted(h.z.x, sz, g.Lz, hi, lo); im.nz.x = -hi; im.nlz.x = -lo;
+    shifted(h.z.y, sz, g.Lz, hi, lo); im.nz.y = -hi; im.nlz.y = -lo;
+    im.shifts = pack_shifts(sx, sy, sz);
+    im.up = (sx > 0) | (sy > 0) | (sz > 0);
+    return im;
+}
+
+// Cold path: the hot loop added the pair's force iff `d2_hot < r2_lo`; take the
+// reference's float64 decision and return the difference (see repair_pair_clusters).
+__device__ __noinline__ float3 repair_pair2(const Geometry& g, float xi, float yi, float zi,
+                                            float nimx, float nimy, float nimz, float nlx,
+                                            float nly, float nlz, int shifts, float xj, float yj,
+                                            float zj, float d2_hot, const PairParam* q)
+{
+    const bool added = d2_hot < g.r2_lo;
+    const double e = exact_dist2(g, xi, yi, zi, xj, yj, zj, shifts);
+    const bool wanted = (1e-10 < e) && (e < g.r2d);
+    if (added == wanted) return make_float3(0.f, 0.f, 0.f);
+    // home - neighbour, from the same operands as the hot loop (signs mirrored exactly)
+    const float dx = -((xj + nimx) + nlx), dy = -((yj + nimy) + nly), dz = -((zj + nimz) + nlz);
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float4 qa = q->a;
+    const float4 qb = q->b;
+    const float inv = fast_rsqrt(d2 + kTinyD2);
+    const float dist = d2 * inv;
+    const float f_in = fmaf(-qa.y, dist, qa.z);
+    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+    float s = (dist < qa.x ? f_in : f_tri) * inv;
+    if (added) s = -s;  // take it back
+    return make_float3(-s * dx, -s * dy, -s * dz);
+}
+
+// One neighbour against the lane's two home particles.  Returns the two squared
+// distances (for the repair vote of the caller).
+template <bool LOWFIX>
+__device__ __forceinline__ float2 neighbour2(Home2& h, PackedParams& pp, const Derived& der,
+                                             const Geometry& g, const Image2& im,
+                                             const float4 A, const float4 B)
+{
+    // neighbour - home (the force below is accumulated with the matching sign)
+    float2 dx = add2(f2(A.x, A.y), im.nx), dy = add2(f2(A.z, A.w), im.ny), dz = add2(f2(B.x, B.y), im.nz);
+    if (LOWFIX) { dx = add2(dx, im.nlx); dy = add2(dy, im.nly); dz = add2(dz, im.nlz); }
+    const float2 d2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, f2(kTinyD2, kTinyD2))));
+    const int tj = __float_as_int(B.z);
+    if (tj != pp.type) load_params(pp, der, h.t0, h.t1, tj);
+    const float2 inv = f2(fast_rsqrt(d2.x), fast_rsqrt(d2.y));
+    const float2 dist = mul2(d2, inv);
+    const float2 u = add2(dist, pp.nrmin);
+    const float2 t = add2(dist, pp.nmid);
+    float2 f = fma2(pp.ns1, f2(fabsf(t.x), fabsf(t.y)), pp.fmax);
+    f = fma2(pp.cc, f2(fminf(u.x, 0.0f), fminf(u.y, 0.0f)), f);
+    const float2 mask = f2(d2.x < g.r2_lo ? 1.0f : 0.0f, d2.y < g.r2_lo ? 1.0f : 0.0f);
+    const float2 s = mul2(mul2(f, inv), mask);
+    // force on home = -f * (home - neighbour) / dist = +s * (neighbour - home); the self
+    // pair contributes s * 0 = 0 with s finite
+    h.ax = fma2(s, dx, h.ax);
+    h.ay = fma2(s, dy, h.ay);
+    h.az = fma2(s, dz, h.az);
+    return d2;
+}
+
+__device__ __forceinline__ bool needs_repair2(const Geometry& g, float2 d2)
+{
+    return needs_repair(g, d2.x) || needs_repair(g, d2.y);
+}
+
+__device__ __forceinline__ void repair2(Home2& h, const PairParam* __restrict__ tab, int T,
+                                        const Geometry& g, const Image2& im, const float4 A,
+                                        const float4 B, float2 d2)
+{
+    const int tj = __float_as_int(B.z);
+    if (needs_repair(g, d2.x)) {
+        const float3 f = repair_pair2(g, h.x.x, h.y.x, h.z.x, im.nx.x, im.ny.x, im.nz.x, im.nlx.x,
+                                      im.nly.x, im.nlz.x, im.shifts, A.x, A.z, B.x, d2.x,
+                                      tab + h.t0 * T + tj);
+        h.ax.x += f.x; h.ay.x += f.y; h.az.x += f.z;
+    }
+    if (needs_repair(g, d2.y)) {
+        const float3 f = repair_pair2(g, h.x.y, h.y.y, h.z.y, im.nx.y, im.ny.y, im.nz.y, im.nlx.y,
+                                      im.nly.y, im.nlz.y, im.shifts, A.x, A.z, B.x, d2.y,
+                                      tab + h.t1 * T + tj);
+        h.ax.y += f.x; h.ay.y += f.y; h.az.y += f.z;
+    }
+}
+
+template <bool LOWFIX>
+__device__ __forceinline__ void run_pairs2(Home2& h, PackedParams& pp, const Derived& der,
+                                           const PairParam* __restrict__ tab, const ForceArgs& a,
+                                           const Geometry& g, const Image2& im, int s, int e)
+{
+    // the run sums into its own accumulators (shorter partial sums: less fp32 rounding)
+    const float2 ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+    h.ax = h.ay = h.az = f2(0.f, 0.f);
+    const float4* __restrict__ da = a.dup_a;
+    const float4* __restrict__ db = a.dup_b;
+    int j = s;
+    for (; j + 2 <= e; j += 2) {
+        const float4 A0 = ldg4(da + j), B0 = ldg4(db + j), A1 = ldg4(da + j + 1), B1 = ldg4(db + j + 1);
+        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, A0, B0);
+        const float2 d1 = neighbour2<LOWFIX>(h, pp, der, g, im, A1, B1);
+        const float lo4 = fminf(fminf(d0.x, d0.y), fminf(d1.x, d1.y));
+        const bool band = (!(d0.x < g.r2_lo) && d0.x < g.r2_hi) | (!(d0.y < g.r2_lo) && d0.y < g.r2_hi) |
+                          (!(d1.x < g.r2_lo) && d1.x < g.r2_hi) | (!(d1.y < g.r2_lo) && d1.y < g.r2_hi);
+        if (band | (lo4 <= 1e-10f)) {
+            if (needs_repair2(g, d0)) repair2(h, tab, der.T, g, im, A0, B0, d0);
+            if (needs_repair2(g, d1)) repair2(h, tab, der.T, g, im, A1, B1, d1);
+        }
+    }
+    if (j < e) {
+        const float4 A0 = ldg4(da + j), B0 = ldg4(db + j);
+        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, A0, B0);
+        if (needs_repair2(g, d0)) repair2(h, tab, der.T, g, im, A0, B0, d0);
+    }
+    h.ax = add2(h.ax, ax0); h.ay = add2(h.ay, ay0); h.az = add2(h.az, az0);
+}
+
+__device__ __forceinline__ void run_image2(Home2& h, PackedParams& pp, const Derived& der,
+                                           const PairParam* __restrict__ tab, const ForceArgs& a,
+                                           const Geometry& g, int sx, int sy, int sz, int s, int e)
+{
+    const Image2 im = make_image2(h, g, sx, sy, sz);
+    if (__any_sync(0xffffffffu, im.up && e > s))
+        run_pairs2<true>(h, pp, der, tab, a, g, im, s, e);
+    else
+        run_pairs2<false>(h, pp, der, tab, a, g, im, s, e);
+}
+
+#ifndef GOF_FORCE2_MINBLOCKS
+#define GOF_FORCE2_MINBLOCKS 4
+#endif
+
+__global__ void __launch_bounds__(kForce2Threads, GOF_FORCE2_MINBLOCKS)
+k_force2(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
+{
+    extern __shared__ float4 smem_raw[];
+    const int T = a.T;
+    PairParam* tab = reinterpret_cast<PairParam*>(smem_raw);  // AoS table: cold paths
+    float4* d4 = reinterpret_cast<float4*>(tab + T * T);
+    float* ccs = reinterpret_cast<float*>(d4 + T * T);
+    for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
+        const PairParam pp = a.table[q];
+        tab[q] = pp;
+        // clusters: a = {r_min, k0, f_min, mid}, b = {s1, f_max}
+        d4[q] = make_float4(-pp.a.x, -pp.a.w, -pp.b.x, pp.b.y);
+        ccs[q] = -pp.a.y - pp.b.x;
+    }
+    __syncthreads();
+    Derived der;
+    der.d4 = d4;
+    der.cc = ccs;
+    der.T = T;
+
+    // padded slot index space: this lane owns slots k0 and k0 + 1 of one cell
+    const int n_pad = a.pstart[g.num_cells];
+    const int slot = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const bool in_range = slot < n_pad;
+    const int k0 = in_range ? slot : 0;
+    const int c = a.cell_sorted[k0];
+    const int first = a.pstart[c], cnt = a.count[c];
+    const bool valid0 = in_range && (k0 - first) < cnt;
+    const bool valid1 = in_range && (k0 + 1 - first) < cnt;  // false: the cell's padding slot
+
+    const float4 p0 = a.posw[k0], p1 = a.posw[k0 + 1];
+    const float4 v0 = a.veli[k0], v1 = a.veli[k0 + 1];
+    Home2 h;
+    h.x = f2(p0.x, p1.x); h.y = f2(p0.y, p1.y); h.z = f2(p0.z, p1.z);
+    h.ax = h.ay = h.az = f2(0.f, 0.f);
+    h.t0 = __float_as_int(p0.w);
+    h.t1 = __float_as_int(p1.w);  // padding slots carry type 0
+    PackedParams pp;
+    pp.type = -1;
+    pp.nrmin = pp.nmid = pp.ns1 = pp.fmax = pp.cc = f2(0.f, 0.f);
+
+    const int cx = c % g.nbx;
+    const int cyz = c / g.nbx;
+    const int cy = cyz % g.nby;
+    const int lz = cyz / g.nby;
+    const int gz = lz + g.layer_base;
+    const bool edge_layer = g.is3d && a.wrap_mode == kWrapReference && (gz == 0 || gz == g.nbz - 1);
+    const bool quirk = __any_sync(0xffffffffu, valid0 && edge_layer);
+
+    const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
+    if (!quirk) {
+        for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
+            int nl = lz + dzi, sz = 0;
+            if (g.is3d) {
+                const int ngz = gz + dzi;
+                if (ngz < 0) { sz = 1; if (g.index_wrap_z) nl += g.nbz; }
+                else if (ngz >= g.nbz) { sz = -1; if (g.index_wrap_z) nl -= g.nbz; }
+            }
+            for (int dyi = -1; dyi <= 1; ++dyi) {
+                int ny = cy + dyi, sy = 0;
+                if (ny < 0) { ny += g.nby; sy = 1; }
+                else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
+                const int rb = (nl * g.nby + ny) * g.nbx;
+                const int lo = cx > 0 ? cx - 1 : 0;
+                const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
+                // padded starts: the run also covers the padding slots of its inner cells,
+                // which sit at 1e18 and fail the distance test like any far particle
+                int s = a.pstart[rb + lo];
+                int e = a.pstart[rb + hi] + a.count[rb + hi];
+                if (!valid0) e = s;
+                run_image2(h, pp, der, tab, a, g, 0, sy, sz, s, e);
+                const bool xedge = cx == 0 || cx == g.nbx - 1;
+                const int wc = cx == 0 ? g.nbx - 1 : 0;
+                s = a.pstart[rb + wc];
+                e = (valid0 && xedge) ? s + a.count[rb + wc] : s;
+                run_image2(h, pp, der, tab, a, g, cx == 0 ? 1 : -1, sy, sz, s, e);
+            }
+        }
+    } else {
+        // reference z-wrap on the bottom / top layer: the literal per-pair path of the
+        // one-home kernel, once per home particle (gof_force.cuh run_pairs_zquirk)
+        for (int which = 0; which < 2; ++which) {
+            const bool valid = which ? valid1 : valid0;
+            Home hs;
+            hs.x = which ? h.x.y : h.x.x; hs.y = which ? h.y.y : h.y.x; hs.z = which ? h.z.y : h.z.x;
+            hs.vx = hs.vy = hs.vz = 0.f;
+            hs.ax = hs.ay = hs.az = 0.f;
+            hs.type = which ? h.t1 : h.t0;
+            hs.kinds = 0u;
+            const PairParam* tabrow = tab + hs.type * T;
+            for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
+                int nl = lz + dzi;
+                const int ngz = gz + dzi;
+                if (g.index_wrap_z) {
+                    if (ngz < 0) nl += g.nbz;
+                    else if (ngz >= g.nbz) nl -= g.nbz;
+                }
+                for (int dyi = -1; dyi <= 1; ++dyi) {
+                    int ny = cy + dyi, sy = 0;
+                    if (ny < 0) { ny += g.nby; sy = 1; }
+                    else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
+                    const int rb = (nl * g.nby + ny) * g.nbx;
+                    for (int dxi = -1; dxi <= 1; ++dxi) {
+                        int nx = cx + dxi, sx = 0;
+                        if (nx < 0) { nx += g.nbx; sx = 1; }
+                        else if (nx >= g.nbx) { nx -= g.nbx; sx = -1; }
+                        const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
+                        const int s = a.pstart[rb + nx];
+                        const int e = valid ? s + a.count[rb + nx] : s;
+                        run_pairs_zquirk<false>(hs, tabrow, nullptr, a, g, s, e, sx, sy, direct);
+                    }
+                }
+            }
+            if (which) { h.ax.y = hs.ax; h.ay.y = hs.ay; h.az.y = hs.az; }
+            else       { h.ax.x = hs.ax; h.ay.x = hs.ay; h.az.x = hs.az; }
+        }
+    }
+
+    // ---- integrator.step2 + boundary_condition (main/integrator.py:58-114), per home ----
+    const int out0 = a.start[c] + (k0 - first);  // compact (unpadded) rest order
+    float sqmax = 0.0f;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const bool valid = which ? valid1 : valid0;
+        const float4 p = which ? p1 : p0;
+        const float4 v = which ? v1 : v0;
+        const float ax = which ? h.ax.y : h.ax.x, ay = which ? h.ay.y : h.ay.x, az = which ? h.az.y : h.az.x;
+        float x = p.x, y = p.y, z = p.z, vx = v.x, vy = v.y, vz = v.z;
+        if (a.integrate) {
+            const float dt = a.scalars->dt;
+            x += (v.x + 0.5f * ax * dt) * dt;
+            y += (v.y + 0.5f * ay * dt) * dt;
+            z += (v.z + 0.5f * az * dt) * dt;
+            vx = fmaf(ax, 0.5f * dt, v.x);
+            vy = fmaf(ay, 0.5f * dt, v.y);
+            vz = fmaf(az, 0.5f * dt, v.z);
+            if (a.self_kind[__float_as_int(p.w)] == 0) { vx *= kDamping; vy *= kDamping; vz *= kDamping; }
+            if (x < 0.0f) x += g.Lx; else if (x > g.Lx) x -= g.Lx;
+            if (y < 0.0f) y += g.Ly; else if (y > g.Ly) y -= g.Ly;
+            if (z < 0.0f) z += g.Lz; else if (z > g.Lz) z -= g.Lz;
+        }
+        if (valid) {
+            const int o = out0 + which;
+            a.posw_out[o] = make_float4(x, y, z, p.w);
+            a.veli_out[o] = make_float4(vx, vy, vz, v.w);
+            a.acc_out[o] = make_float4(ax, ay, az, 0.0f);
+            sqmax = fmaxf(sqmax, vx * vx + vy * vy + vz * vz);
+        }
+    }
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(sqmax));
+    if (lane_id() == 0) atomicMax(&a.scalars->max_sq_speed_bits[a.parity_out], m);
+}
+
+}  // namespace gof

@@ -183,6 +183,14 @@ int gof_engine_snapshot(gof_engine *e, float *xyz_any, void *stream);
 int gof_engine_read_bins(gof_engine *e, int32_t *particle_bins_any, int32_t *bin_counts_any,
                          int32_t *bin_starts_any, int32_t *particle_indices_any, void *stream);
 
+/* Force-kernel selection.  GOF_KERNEL_SCALAR (default): one home particle per lane, any mix
+ * of Clusters and Boids species.  GOF_KERNEL_PACKED: two home particles per lane with packed
+ * fp32 arithmetic; used only while every species pair is of the Clusters kind, otherwise the
+ * engine falls back to the scalar kernel.  Results agree to fp32 rounding. */
+#define GOF_KERNEL_SCALAR 0
+#define GOF_KERNEL_PACKED 1
+int gof_engine_set_kernel(gof_engine *e, int kernel);
+
 /* Per-kernel timing for bench.py's roofline: when enabled, gof_engine_step brackets every
  * force-kernel launch with CUDA events on `stream` (up to 4096 launches per enable).
  * gof_engine_force_time synchronises on the recorded events and returns the summed
