@@ -704,6 +704,17 @@ struct gof_engine {
     int* stage_indices = nullptr;
     float* stage_xyz = nullptr;    // snapshot [N][3]
 
+    // slab mode (multi-GPU): this engine owns the global z-layers [layer_lo, layer_hi)
+    bool slab = false;
+    int layer_lo = 0, layer_hi = 0;
+    int mig_capacity = 0;   // migration records per direction
+    int halo_capacity = 0;  // halo particles per side
+    float4 *mig_send[2] = {nullptr, nullptr};  // [0] down, [1] up
+    float4 *mig_recv[2] = {nullptr, nullptr};  // [0] from the slab below, [1] from above
+    int* counters = nullptr;                   // MigrateOut counters (4 ints)
+    int n_slots = 0;        // resident slots before the sort (live + dead + arrivals)
+    int n_halo[2] = {0, 0};
+
     // optional per-launch timing of the force kernel (bench.py roofline)
     bool timing = false;
     std::vector<cudaEvent_t> ev;  // pairs: start, stop
@@ -723,7 +734,8 @@ static size_t engine_layout(gof_engine* e, char* base)
     };
     const size_t cap = (size_t)e->capacity;
     const size_t cells = (size_t)e->geom.num_cells + 2;
-    const size_t slots = cap + cells;  // padded snapshot: at most one extra slot per cell
+    // padded snapshot: at most one extra slot per cell; slab mode appends the two halo layers
+    const size_t slots = cap + cells + 2 * (size_t)e->halo_capacity;
     e->slot_capacity = (int)slots;
     // [0] = rest state (compact, last step's cell order), [1] = this step's snapshot (padded slots)
     e->posw[0] = (float4*)take(cap * sizeof(float4));
@@ -750,6 +762,13 @@ static size_t engine_layout(gof_engine* e, char* base)
     e->stage_bins = (int*)take(cap * sizeof(int));
     e->stage_indices = (int*)take(cap * sizeof(int));
     e->stage_xyz = (float*)take(cap * 3 * sizeof(float));
+    if (e->slab) {
+        for (int d = 0; d < 2; ++d) {
+            e->mig_send[d] = (float4*)take((size_t)e->mig_capacity * 3 * sizeof(float4));
+            e->mig_recv[d] = (float4*)take((size_t)e->mig_capacity * 3 * sizeof(float4));
+        }
+        e->counters = (int*)take(4 * sizeof(int));
+    }
     return o;
 }
 
@@ -918,7 +937,7 @@ static int engine_bin(gof_engine* e, bool kick, cudaStream_t st)
 static int engine_force(gof_engine* e, const ForceArgs& a, cudaStream_t st)
 {
     if (engine_packed(e)) return launch_force2(e->geom, a, e->n + e->geom.num_cells, st);
-    return launch_force(e->geom, a, true, kModeIntegrate, st);
+    return launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st);
 }
 
 static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
@@ -1047,5 +1066,284 @@ extern "C" int gof_engine_last_timestep(gof_engine* e, float* out, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     GOF_CUDA(cudaMemcpyAsync(out, &e->scalars->dt, sizeof(float), cudaMemcpyDeviceToHost, st));
     GOF_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// slab decomposition (multi-GPU): one engine per z-slab, host exchanges via NCCL send/recv
+// --------------------------------------------------------------------------------------
+extern "C" int gof_slab_create(gof_engine** out, int device, int capacity, int num_types,
+                               const gof_grid* grid, const double* pm_host, int layer_lo, int layer_hi,
+                               int migrate_capacity, int halo_capacity)
+{
+    if (!out || capacity < 1 || !grid) return fail(GOF_E_INVALID, "gof_slab_create: bad arguments");
+    if (grid->num_bin_z < 4) return fail(GOF_E_GRID, "gof_slab_create: slab decomposition needs a 3D box with >= 4 layers");
+    const int owned = layer_hi - layer_lo;
+    if (layer_lo < 0 || layer_hi > grid->num_bin_z || owned < 1 || owned > grid->num_bin_z - 2)
+        return fail(GOF_E_INVALID, "gof_slab_create: a slab owns between 1 and num_bin_z - 2 layers");
+    if (migrate_capacity < 1 || halo_capacity < 1) return fail(GOF_E_INVALID, "gof_slab_create: bad capacities");
+    gof_engine* e = new (std::nothrow) gof_engine();
+    if (!e) return fail(GOF_E_NOMEM, "gof_slab_create: host allocation failed");
+    e->device = device;
+    e->capacity = capacity;
+    e->n = 0;
+    e->T = num_types;
+    e->grid = *grid;
+    e->slab = true;
+    e->layer_lo = layer_lo;
+    e->layer_hi = layer_hi;
+    e->mig_capacity = migrate_capacity;
+    e->halo_capacity = halo_capacity;
+    int rc = make_geometry(grid, layer_lo - 1, owned + 2, &e->geom);
+    if (!rc) rc = build_species(pm_host, num_types, &e->species);
+    if (rc) {
+        delete e;
+        return rc;
+    }
+    e->arena_bytes = engine_layout(e, nullptr);
+    *out = e;
+    return 0;
+}
+
+namespace gof {
+// slab upload: SoA + explicit global ids -> float4 state, and the maximum squared speed
+__global__ void __launch_bounds__(kEwThreads)
+k_pack_ids(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
+           const float* __restrict__ vx, const float* __restrict__ vy, const float* __restrict__ vz,
+           const float* __restrict__ ax, const float* __restrict__ ay, const float* __restrict__ az,
+           const int* __restrict__ types, const int* __restrict__ ids, int n, float4* __restrict__ posw,
+           float4* __restrict__ veli, float4* __restrict__ acc, unsigned* __restrict__ max_bits)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.0f;
+    if (i < n) {
+        const float4 v = make_float4(vx ? vx[i] : 0.f, vy ? vy[i] : 0.f, vz ? vz[i] : 0.f, __int_as_float(ids[i]));
+        posw[i] = make_float4(px[i], py[i], pz[i], __int_as_float(types[i]));
+        veli[i] = v;
+        acc[i] = make_float4(ax ? ax[i] : 0.f, ay ? ay[i] : 0.f, az ? az[i] : 0.f, 0.f);
+        sq = v.x * v.x + v.y * v.y + v.z * v.z;
+    }
+    const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(sq));
+    if (lane_id() == 0) atomicMax(max_bits, w);
+}
+
+// rest order -> SoA staging without un-permuting (slab download: the host scatters by id)
+__global__ void __launch_bounds__(kEwThreads)
+k_unpack_rest(const float4* __restrict__ posw, const float4* __restrict__ veli, const float4* __restrict__ acc,
+              int n, float* __restrict__ px, float* __restrict__ py, float* __restrict__ pz,
+              float* __restrict__ vx, float* __restrict__ vy, float* __restrict__ vz,
+              float* __restrict__ ax, float* __restrict__ ay, float* __restrict__ az, int* __restrict__ ids)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 p = posw[k], v = veli[k], a = acc[k];
+    px[k] = p.x; py[k] = p.y; pz[k] = p.z;
+    vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
+    ax[k] = a.x; ay[k] = a.y; az[k] = a.z;
+    ids[k] = __float_as_int(v.w);
+}
+}  // namespace gof
+
+static int slab_ready(gof_engine* e, bool need_state)
+{
+    if (int rc = engine_ready(e, need_state)) return rc;
+    if (!e->slab) return fail(GOF_E_STATE, "not a slab engine (use gof_slab_create)");
+    return 0;
+}
+
+extern "C" int gof_slab_upload(gof_engine* e, int n, const float* px, const float* py, const float* pz,
+                               const float* vx, const float* vy, const float* vz, const float* ax,
+                               const float* ay, const float* az, const int32_t* types, const int32_t* ids,
+                               void* stream)
+{
+    if (int rc = slab_ready(e, false)) return rc;
+    if (n < 0 || n > e->capacity) return fail(GOF_E_NOMEM, "gof_slab_upload: more particles than capacity");
+    if (n > 0 && (!px || !py || !pz || !types || !ids)) return fail(GOF_E_INVALID, "gof_slab_upload: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* src[9] = {px, py, pz, vx, vy, vz, ax, ay, az};
+    for (int k = 0; k < 9; ++k)
+        if (src[k] && n) GOF_CUDA(cudaMemcpyAsync(e->stage[k], src[k], (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    if (n) {
+        GOF_CUDA(cudaMemcpyAsync(e->stage_types, types, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
+        GOF_CUDA(cudaMemcpyAsync(e->stage_bins, ids, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
+    }
+    if (e->species_dirty) {
+        if (int rc = upload_species(e->species, e->dspecies, st)) return rc;
+        e->species_dirty = false;
+    }
+    GOF_CUDA(cudaMemsetAsync(e->scalars, 0, sizeof(StepScalars), st));
+    e->parity = 0;
+    e->n = n;
+    if (n)
+        GOF_LAUNCH(k_pack_ids, cdiv(n, kEwThreads), kEwThreads, 0, st, e->stage[0], e->stage[1], e->stage[2],
+                   vx ? e->stage[3] : nullptr, vy ? e->stage[4] : nullptr, vz ? e->stage[5] : nullptr,
+                   ax ? e->stage[6] : nullptr, ay ? e->stage[7] : nullptr, az ? e->stage[8] : nullptr,
+                   e->stage_types, e->stage_bins, n, e->posw[0], e->veli[0], e->acc,
+                   &e->scalars->max_sq_speed_bits[0]);
+    e->uploaded = true;
+    e->binned = false;
+    return 0;
+}
+
+/* Device pointers the host wraps as tensors for send/recv (all inside the bound arena). */
+extern "C" int gof_slab_pointers(gof_engine* e, void** ptrs, int n_ptrs)
+{
+    if (int rc = slab_ready(e, false)) return rc;
+    if (!ptrs || n_ptrs < 10) return fail(GOF_E_INVALID, "gof_slab_pointers: need room for 10 pointers");
+    ptrs[0] = e->mig_send[0];
+    ptrs[1] = e->mig_send[1];
+    ptrs[2] = e->mig_recv[0];
+    ptrs[3] = e->mig_recv[1];
+    ptrs[4] = e->posw[1];
+    ptrs[5] = e->veli[1];
+    ptrs[6] = e->count;
+    ptrs[7] = &e->scalars->max_sq_speed_bits[0];
+    ptrs[8] = &e->scalars->max_sq_speed_bits[1];
+    ptrs[9] = e->start;
+    return 0;
+}
+
+/* Phase 1: bin the resident particles; the ones that left the slab are packed into the
+ * send buffers.  Synchronises `stream`; out_counts = {going down, going up}. */
+extern "C" int gof_slab_phase_hash(gof_engine* e, int* out_counts, void* stream)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    if (!out_counts) return fail(GOF_E_INVALID, "gof_slab_phase_hash: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geometry& g = e->geom;
+    GOF_CUDA(cudaMemsetAsync(e->count, 0, (size_t)(g.num_cells + 2) * sizeof(int), st));
+    GOF_CUDA(cudaMemsetAsync(e->counters, 0, 4 * sizeof(int), st));
+    if (e->n > 0) {
+        MigrateOut mig{e->mig_send[0], e->mig_send[1], e->counters, e->mig_capacity};
+        GOF_LAUNCH(k_hash_count<false>, cdiv(e->n, kBinThreads), kBinThreads, 0, st, e->posw[0], e->veli[0], e->acc,
+                   (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, e->n, g, e->cell_of, e->off,
+                   e->count, mig);
+    }
+    int h[4] = {0, 0, 0, 0};
+    GOF_CUDA(cudaMemcpyAsync(h, e->counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GOF_CUDA(cudaStreamSynchronize(st));
+    if (h[2] == 1) return fail(GOF_E_STATE, "slab: a particle moved more than one layer in a step");
+    if (h[2] == 2 || h[0] > e->mig_capacity || h[1] > e->mig_capacity)
+        return fail(GOF_E_NOMEM, "slab: migration buffer overflow (raise migrate_capacity)");
+    out_counts[0] = h[0];
+    out_counts[1] = h[1];
+    e->n_slots = e->n;
+    return 0;
+}
+
+/* Phase 2: append the arrivals (already received into the recv buffers), bin them, sort
+ * everything by cell and kick the velocities.  The maximum squared speed must have been
+ * all-reduced over the slabs before this call when the timestep is adaptive.
+ * Synchronises; out_counts = {live particles, population of the bottom owned layer, of the top one}. */
+extern "C" int gof_slab_phase_sort(gof_engine* e, int n_from_down, int n_from_up, float timestep,
+                                   int* out_counts, void* stream)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    if (!out_counts || n_from_down < 0 || n_from_up < 0) return fail(GOF_E_INVALID, "gof_slab_phase_sort: bad arguments");
+    if (n_from_down > e->mig_capacity || n_from_up > e->mig_capacity)
+        return fail(GOF_E_NOMEM, "slab: more arrivals than migrate_capacity");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geometry& g = e->geom;
+    const int arrivals = n_from_down + n_from_up;
+    const int total = e->n_slots + arrivals;
+    if (total > e->capacity) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
+    if (arrivals > 0) {
+        GOF_LAUNCH(k_append_arrivals, cdiv(arrivals, kBinThreads), kBinThreads, 0, st, e->mig_recv[0], n_from_down,
+                   e->mig_recv[1], n_from_up, e->n_slots, e->posw[0], e->veli[0], e->acc);
+        MigrateOut flag_only{nullptr, nullptr, e->counters, 0};
+        GOF_LAUNCH(k_hash_count<false>, cdiv(arrivals, kBinThreads), kBinThreads, 0, st, e->posw[0] + e->n_slots,
+                   e->veli[0] + e->n_slots, e->acc + e->n_slots, (const float*)nullptr, (const float*)nullptr,
+                   (const float*)nullptr, arrivals, g, e->cell_of + e->n_slots, e->off + e->n_slots, e->count,
+                   flag_only);
+    }
+    GOF_LAUNCH(k_prepare_dt, 1, 1, 0, st, e->scalars, e->parity, timestep < 0 ? -1.0f : timestep);
+    if (int rc = launch_scan<false>(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
+    if (total > 0) {
+        GOF_LAUNCH(k_scatter_ids<false>, cdiv(total, kBinThreads), kBinThreads, 0, st, e->veli[0], total, e->cell_of,
+                   e->off, e->start, e->slot_id);
+        GOF_LAUNCH(k_rank_gather_kick, cdiv(total, kBinThreads), kBinThreads, 0, st, total, e->cell_of, e->start,
+                   e->count, e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1],
+                   e->cell_sorted, (float4*)nullptr, (float4*)nullptr, e->scalars, 1);
+    }
+    // live count and the populations of the two owned boundary layers, from the start table
+    const int per_layer = g.nbx * g.nby;
+    const int top = g.nlz - 2;  // local index of the top owned layer
+    int h[5];
+    const int idx[4] = {g.num_cells, 2 * per_layer, top * per_layer, (top + 1) * per_layer};
+    for (int k = 0; k < 4; ++k)
+        GOF_CUDA(cudaMemcpyAsync(&h[k], e->start + idx[k], sizeof(int), cudaMemcpyDeviceToHost, st));
+    GOF_CUDA(cudaMemcpyAsync(&h[4], &e->counters[2], sizeof(int), cudaMemcpyDeviceToHost, st));
+    GOF_CUDA(cudaStreamSynchronize(st));
+    if (h[4] != 0) return fail(GOF_E_STATE, "slab: an arriving particle does not belong to this slab");
+    const int n_live = h[0];
+    out_counts[0] = n_live;
+    out_counts[1] = (top >= 2) ? h[1] : n_live;           // bottom owned layer = local layer 1 (starts at 0)
+    out_counts[2] = (top >= 2) ? h[3] - h[2] : n_live;    // top owned layer
+    if (out_counts[1] > e->halo_capacity || out_counts[2] > e->halo_capacity)
+        return fail(GOF_E_NOMEM, "slab: boundary layer larger than halo_capacity");
+    e->n = n_live;
+    e->binned = true;
+    e->binned_packed = false;
+    return 0;
+}
+
+/* Phase 3: the halo particles (n_lo from the slab below, then n_hi from the slab above)
+ * have been received behind the owned ones and their per-cell counts into the count rows
+ * of the two halo layers.  Forces + integration of the owned particles. */
+extern "C" int gof_slab_phase_force(gof_engine* e, int n_halo_lo, int n_halo_hi, int wrap_mode, void* stream)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    if (n_halo_lo < 0 || n_halo_hi < 0 || n_halo_lo > e->halo_capacity || n_halo_hi > e->halo_capacity)
+        return fail(GOF_E_NOMEM, "slab: halo larger than halo_capacity");
+    if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
+        return fail(GOF_E_INVALID, "gof_slab_phase_force: bad wrap_mode");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geometry& g = e->geom;
+    const int per_layer = g.nbx * g.nby;
+    GOF_LAUNCH(k_halo_starts, 2, kScanThreads, 0, st, e->count, e->start, per_layer, (g.nlz - 1) * per_layer, e->n,
+               e->n + n_halo_lo);
+    ForceArgs a;
+    engine_force_args(e, wrap_mode, &a);
+    a.pstart = e->start;
+    a.integrate = 1;
+    a.parity_out = e->parity ^ 1;
+    const bool timed = e->timing && e->ev_used < kMaxTimedLaunches;
+    if (timed) {
+        while ((int)e->ev.size() < 2 * (e->ev_used + 1)) {
+            cudaEvent_t v;
+            GOF_CUDA(cudaEventCreate(&v));
+            e->ev.push_back(v);
+        }
+        GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used], st));
+    }
+    if (int rc = launch_force(g, a, e->species.has_boids, kModeIntegrate, st)) return rc;
+    if (timed) {
+        GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used + 1], st));
+        ++e->ev_used;
+    }
+    e->parity ^= 1;
+    return 0;
+}
+
+/* Current parity (which of the two max-speed slots describes the resident velocities). */
+extern "C" int gof_slab_parity(const gof_engine* e) { return e ? e->parity : 0; }
+extern "C" int gof_slab_count(const gof_engine* e) { return e ? e->n : 0; }
+
+/* State in rest order with the particle ids (the host scatters by id).  Arrays hold
+ * gof_slab_count() entries; pointers may be host or device. */
+extern "C" int gof_slab_download(gof_engine* e, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
+                                 float* ax, float* ay, float* az, int32_t* ids, void* stream)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = e->n;
+    if (n == 0) return 0;
+    GOF_LAUNCH(k_unpack_rest, cdiv(n, kEwThreads), kEwThreads, 0, st, e->posw[0], e->veli[0], e->acc, n, e->stage[0],
+               e->stage[1], e->stage[2], e->stage[3], e->stage[4], e->stage[5], e->stage[6], e->stage[7],
+               e->stage[8], e->stage_bins);
+    float* dst[9] = {px, py, pz, vx, vy, vz, ax, ay, az};
+    for (int k = 0; k < 9; ++k)
+        if (dst[k]) GOF_CUDA(cudaMemcpyAsync(dst[k], e->stage[k], (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    if (ids) GOF_CUDA(cudaMemcpyAsync(ids, e->stage_bins, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
     return 0;
 }

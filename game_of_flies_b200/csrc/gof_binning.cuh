@@ -22,13 +22,14 @@ constexpr int kScanThreads = 1024;
 constexpr int kScanItems = 4;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
-// Slab-mode send buffers for particles that left the owned layers (START-of-step
-// migration; see slab.py).  All pointers may be null on a single GPU.
+// Slab-mode send buffers for particles that left the owned layers (start-of-step
+// migration; see game_of_flies_b200/slab.py).  A record is three float4: {x, y, z, type},
+// {vx, vy, vz, id}, {ax, ay, az, 0}.  All pointers are null on a single GPU.
 struct MigrateOut {
-    float4* down_posw; float4* down_veli; float4* down_acc;
-    float4* up_posw;   float4* up_veli;   float4* up_acc;
+    float4* down;    // records for the slab below
+    float4* up;      // records for the slab above
     int* counters;   // [0] = number going down, [1] = going up, [2] = error flag
-    int capacity;
+    int capacity;    // records per buffer
 };
 
 // Cell of every particle + per-cell population.  One atomic per distinct cell per
@@ -77,14 +78,17 @@ k_hash_count(const float4* __restrict__ posw, const float4* __restrict__ veli,
                 // slab mode: a particle in a halo layer has left; hand it to the neighbour
                 const bool down = (lz == 0), up = (lz == g.nlz - 1);
                 if (down || up || lz >= g.nlz) {
-                    if (lz >= g.nlz || mig.counters == nullptr) {
+                    if (lz >= g.nlz || mig.down == nullptr) {
+                        // more than one layer away, or an arrival that is not ours: cannot happen
+                        // while a step moves a particle by far less than a bin (speed is capped)
                         if (mig.counters) atomicExch(&mig.counters[2], 1);
                     } else {
                         const int k = atomicAdd(&mig.counters[down ? 0 : 1], 1);
                         if (k < mig.capacity) {
-                            (down ? mig.down_posw : mig.up_posw)[k] = posw[i];
-                            (down ? mig.down_veli : mig.up_veli)[k] = veli[i];
-                            (down ? mig.down_acc : mig.up_acc)[k] = acc[i];
+                            float4* rec = (down ? mig.down : mig.up) + 3 * (size_t)k;
+                            rec[0] = posw[i];
+                            rec[1] = veli[i];
+                            rec[2] = acc[i];
                         } else {
                             atomicExch(&mig.counters[2], 2);
                         }
@@ -302,6 +306,44 @@ k_rank_gather_kick(int n, const int* __restrict__ cell_of, const int* __restrict
             dup_a[dst + 1] = make_float4(D, D, D, D);
             dup_b[dst + 1] = make_float4(D, D, __int_as_float(0), 0.0f);
         }
+    }
+}
+
+}  // namespace gof
+
+namespace gof {
+
+// Slab mode: unpack the migration records received from the two neighbours behind the
+// resident particles (they are binned with the rest right after).
+__global__ void __launch_bounds__(kBinThreads)
+k_append_arrivals(const float4* __restrict__ from_down, int n_down, const float4* __restrict__ from_up,
+                  int n_up, int base, float4* __restrict__ posw, float4* __restrict__ veli,
+                  float4* __restrict__ acc)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_down + n_up) return;
+    const float4* rec = k < n_down ? from_down + 3 * (size_t)k : from_up + 3 * (size_t)(k - n_down);
+    posw[base + k] = rec[0];
+    veli[base + k] = rec[1];
+    acc[base + k] = rec[2];
+}
+
+// Slab mode: first index of every cell of the two halo layers.  The halo particles were
+// received behind the owned ones (lower halo at `base_lo`, upper at `base_hi`), cell by
+// cell in the sender's order, together with the per-cell counts.  One block per layer.
+__global__ void __launch_bounds__(kScanThreads)
+k_halo_starts(const int* __restrict__ count, int* __restrict__ start, int cells_per_layer,
+              int first_cell_hi, int base_lo, int base_hi)
+{
+    const int first = blockIdx.x ? first_cell_hi : 0;
+    int carry = blockIdx.x ? base_hi : base_lo;
+    for (int b = 0; b < cells_per_layer; b += kScanThreads) {
+        const int idx = b + threadIdx.x;
+        const int v = idx < cells_per_layer ? count[first + idx] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, total);
+        if (idx < cells_per_layer) start[first + idx] = carry + ex;
+        carry += total;
     }
 }
 

@@ -338,8 +338,9 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
     h.ax += ax0; h.ay += ay0; h.az += az0;
 }
 
-// Warp-uniform choice of the LOWFIX variant: callers are convergent (every lane walks the
-// same sequence of runs, possibly empty), so the vote is safe and costs no divergence.
+// Choice of the LOWFIX variant for the lanes that are converged here (every lane of a code
+// path walks the same sequence of runs, possibly empty).  The variant does not change a
+// lane's result when its own `lo` parts are zero, so the vote only saves instructions.
 template <bool BOIDS>
 __device__ __forceinline__ void run_image(Home& h, RowAddr tabrow_s,
                                           const PairParam* __restrict__ tabrow,
@@ -347,7 +348,11 @@ __device__ __forceinline__ void run_image(Home& h, RowAddr tabrow_s,
                                           const Geometry& g, int sx, int sy, int sz, int s, int e)
 {
     const Image im = make_image(h, g, sx, sy, sz);
-    if (__any_sync(0xffffffffu, im.up && e > s))
+#ifdef GOF_LOWFIX_ALWAYS
+    if (true)
+#else
+    if (__any_sync(__activemask(), im.up && e > s))
+#endif
         run_pairs<BOIDS, true>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
     else
         run_pairs<BOIDS, false>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
@@ -461,10 +466,11 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     const int lz = cyz / g.nby;
     const int gz = lz + g.layer_base;  // global layer
 
-    // does this warp need the literal z-wrap path?
-    const bool edge_layer = g.is3d && a.wrap_mode == kWrapReference &&
-                            (gz == 0 || gz == g.nbz - 1);
-    const bool quirk = __any_sync(0xffffffffu, valid && edge_layer);
+    // Home cells on the bottom / top layer take the literal z-wrap path.  The choice is made
+    // PER LANE (a warp that straddles the layer boundary runs both paths one after the other):
+    // what a particle computes must not depend on its warp-mates, or the result would change
+    // with the decomposition.  The votes inside the fast path use the active mask.
+    const bool quirk = g.is3d && a.wrap_mode == kWrapReference && (gz == 0 || gz == g.nbz - 1);
 
     const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
     if (!quirk) {
@@ -509,16 +515,33 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 if (ny < 0) { ny += g.nby; sy = 1; }
                 else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
                 const int rb = (nl * g.nby + ny) * g.nbx;
-                for (int dxi = -1; dxi <= 1; ++dxi) {
-                    int nx = cx + dxi, sx = 0;
-                    if (nx < 0) { nx += g.nbx; sx = 1; }
-                    else if (nx >= g.nbx) { nx -= g.nbx; sx = -1; }
+                // Same run structure and partial sums as the fast path (the un-shifted x cells
+                // in ascending order, then the cell across the x boundary), so that a particle's
+                // result does not depend on which path its warp-mates forced it through.
+                const int lo = cx > 0 ? cx - 1 : 0;
+                const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
+                float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+                h.ax = h.ay = h.az = 0.0f;
+                for (int nx = lo; nx <= hi; ++nx) {
+                    const int dxi = nx - cx;
                     // half stencil of set_bin_neighbours (acceleration_updater.py:140-215)
                     const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
                     const int s = a.pstart[rb + nx];
                     const int e = valid ? s + a.count[rb + nx] : s;
-                    run_pairs_zquirk<BOIDS>(h, tabrow, boid_acc, a, g, s, e, sx, sy, direct);
+                    run_pairs_zquirk<BOIDS>(h, tabrow, boid_acc, a, g, s, e, 0, sy, direct);
                 }
+                h.ax += ax0; h.ay += ay0; h.az += az0;
+                ax0 = h.ax; ay0 = h.ay; az0 = h.az;
+                h.ax = h.ay = h.az = 0.0f;
+                if (cx == 0 || cx == g.nbx - 1) {
+                    const int wc = cx == 0 ? g.nbx - 1 : 0;
+                    const int dxi = cx == 0 ? -1 : 1;
+                    const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
+                    const int s = a.pstart[rb + wc];
+                    const int e = valid ? s + a.count[rb + wc] : s;
+                    run_pairs_zquirk<BOIDS>(h, tabrow, boid_acc, a, g, s, e, cx == 0 ? 1 : -1, sy, direct);
+                }
+                h.ax += ax0; h.ay += ay0; h.az += az0;
             }
         }
     }

@@ -204,7 +204,7 @@ __device__ __forceinline__ void run_image2(Home2& h, PackedParams& pp, const Der
                                            const Geometry& g, int sx, int sy, int sz, int s, int e)
 {
     const Image2 im = make_image2(h, g, sx, sy, sz);
-    if (__any_sync(0xffffffffu, im.up && e > s))
+    if (__any_sync(__activemask(), im.up && e > s))
         run_pairs2<true>(h, pp, der, tab, a, g, im, s, e);
     else
         run_pairs2<false>(h, pp, der, tab, a, g, im, s, e);
@@ -261,8 +261,8 @@ k_force2(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a
     const int cy = cyz % g.nby;
     const int lz = cyz / g.nby;
     const int gz = lz + g.layer_base;
-    const bool edge_layer = g.is3d && a.wrap_mode == kWrapReference && (gz == 0 || gz == g.nbz - 1);
-    const bool quirk = __any_sync(0xffffffffu, valid0 && edge_layer);
+    // per lane, like the one-home kernel: a particle's arithmetic never depends on warp-mates
+    const bool quirk = g.is3d && a.wrap_mode == kWrapReference && (gz == 0 || gz == g.nbz - 1);
 
     const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
     if (!quirk) {
@@ -317,15 +317,30 @@ k_force2(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a
                     if (ny < 0) { ny += g.nby; sy = 1; }
                     else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
                     const int rb = (nl * g.nby + ny) * g.nbx;
-                    for (int dxi = -1; dxi <= 1; ++dxi) {
-                        int nx = cx + dxi, sx = 0;
-                        if (nx < 0) { nx += g.nbx; sx = 1; }
-                        else if (nx >= g.nbx) { nx -= g.nbx; sx = -1; }
+                    // same run structure and partial sums as the fast path
+                    const int lo = cx > 0 ? cx - 1 : 0;
+                    const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
+                    float ax0 = hs.ax, ay0 = hs.ay, az0 = hs.az;
+                    hs.ax = hs.ay = hs.az = 0.0f;
+                    for (int nx = lo; nx <= hi; ++nx) {
+                        const int dxi = nx - cx;
                         const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
                         const int s = a.pstart[rb + nx];
                         const int e = valid ? s + a.count[rb + nx] : s;
-                        run_pairs_zquirk<false>(hs, tabrow, nullptr, a, g, s, e, sx, sy, direct);
+                        run_pairs_zquirk<false>(hs, tabrow, nullptr, a, g, s, e, 0, sy, direct);
                     }
+                    hs.ax += ax0; hs.ay += ay0; hs.az += az0;
+                    ax0 = hs.ax; ay0 = hs.ay; az0 = hs.az;
+                    hs.ax = hs.ay = hs.az = 0.0f;
+                    if (cx == 0 || cx == g.nbx - 1) {
+                        const int wc = cx == 0 ? g.nbx - 1 : 0;
+                        const int dxi = cx == 0 ? -1 : 1;
+                        const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
+                        const int s = a.pstart[rb + wc];
+                        const int e = valid ? s + a.count[rb + wc] : s;
+                        run_pairs_zquirk<false>(hs, tabrow, nullptr, a, g, s, e, cx == 0 ? 1 : -1, sy, direct);
+                    }
+                    hs.ax += ax0; hs.ay += ay0; hs.az += az0;
                 }
             }
             if (which) { h.ax.y = hs.ax; h.ay.y = hs.ay; h.az.y = hs.az; }

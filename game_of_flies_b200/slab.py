@@ -1,0 +1,378 @@
+"""Slab decomposition of the periodic box over several GPUs.
+
+For N beyond one GPU's sweet spot the box is cut along z into slabs of whole bin
+layers.  Each slab is one `SlabEngine` (one GPU, normally one process): it owns the
+particles whose bin layer lies in [layer_lo, layer_hi) and, per step,
+
+  1. bins its particles and hands the ones that left to the neighbouring slabs
+     (particle migration: records of position+type, velocity+id, acceleration);
+  2. sorts by cell, then exchanges its two boundary layers with the neighbours
+     (halo-cell exchange: cell-ordered positions, velocities and per-cell counts,
+     contiguous slices of the sorted arrays, so nothing is packed);
+  3. computes forces for the owned particles over the local grid (owned layers +
+     one halo layer each side) and integrates.
+
+`SlabRunner` sequences these phases and moves the buffers: with NCCL send/recv
+over NVLink when every process drives one slab (`DistComm`), or with plain device
+copies when several slabs live in one process (`LocalComm`, used to test the CUDA
+path on a single GPU).  The only collectives are tiny: an all-gather of the
+message sizes twice per step and, with the adaptive timestep, a MAX all-reduce of
+one word.  The physics is that of the single-GPU engine, bit for bit: the same
+cells, the same order inside a cell (by particle id), the same summation order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def split_layers(num_layers: int, world: int):
+    """Contiguous, near-equal ranges of z-layers, one per slab."""
+    if world < 2:
+        raise ValueError("slab decomposition needs at least 2 slabs")
+    if num_layers < 2 * world or num_layers < 4:
+        raise ValueError(f"{num_layers} bin layers along z cannot be cut into {world} slabs "
+                         "(every slab needs >= 2 layers and the box >= 4)")
+    bounds = [(r * num_layers) // world for r in range(world + 1)]
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+class SlabEngine:
+    """One z-slab on one CUDA device (gof_slab_* entry points of include/gof_b200.h)."""
+
+    REC = 12  # floats per migration record
+
+    def __init__(self, parameter_matrix, limits, r_max, layer_lo, layer_hi, capacity,
+                 migrate_capacity=None, halo_capacity=None, device=None,
+                 wrap_mode=_lib.WRAP_REFERENCE):
+        from .device import _require_cuda
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        pm = np.ascontiguousarray(parameter_matrix, dtype=np.float64)
+        self.num_types = int(pm.shape[1])
+        self.grid = _lib.make_grid(limits, r_max)
+        self.layer_lo, self.layer_hi = int(layer_lo), int(layer_hi)
+        self.nlz = self.layer_hi - self.layer_lo + 2
+        self.per_layer = int(self.grid.num_bin_x) * int(self.grid.num_bin_y)
+        self.capacity = int(capacity)
+        owned = self.layer_hi - self.layer_lo
+        mean_layer = max(1, self.capacity // max(owned, 1))
+        self.halo_capacity = int(halo_capacity or 4 * mean_layer + 1024)
+        self.migrate_capacity = int(migrate_capacity or max(4096, mean_layer))
+        self.wrap_mode = int(wrap_mode)
+        self._handle = C.c_void_p()
+        _lib.check(self.lib.gof_slab_create(C.byref(self._handle), self.index, self.capacity, self.num_types,
+                                            C.byref(self.grid), pm.ctypes.data, self.layer_lo, self.layer_hi,
+                                            self.migrate_capacity, self.halo_capacity))
+        nbytes = int(self.lib.gof_engine_arena_bytes(self._handle))
+        with torch.cuda.device(self.index):
+            self.arena = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+        self._arena_ptr = (self.arena.data_ptr() + 255) // 256 * 256
+        _lib.check(self.lib.gof_engine_bind_arena(self._handle, self._arena_ptr, nbytes))
+        ptrs = (C.c_void_p * 10)()
+        _lib.check(self.lib.gof_slab_pointers(self._handle, ptrs, 10))
+        self._ptr = [int(p or 0) for p in ptrs]
+        self.n_live = 0
+        self.lo_pop = self.hi_pop = 0
+
+    # ---- helpers ----------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.index).cuda_stream
+
+    def _view(self, ptr: int, count: int, dtype) -> torch.Tensor:
+        """`count` elements of `dtype` at device address `ptr` (inside the arena) as a tensor."""
+        item = torch.empty((), dtype=dtype).element_size()
+        off = ptr - self.arena.data_ptr()
+        return self.arena[off: off + count * item].view(dtype)
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            torch.cuda.synchronize(self.index)
+            self.lib.gof_engine_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state -------------------------------------------------------------------------------
+    def upload(self, pos, types, ids, vel=None, acc=None):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        p = [f(a) for a in pos]
+        v = [f(a) for a in vel] if vel is not None else [None] * 3
+        a_ = [f(a) for a in acc] if acc is not None else [None] * 3
+        t = np.ascontiguousarray(types, dtype=np.int32)
+        i = np.ascontiguousarray(ids, dtype=np.int32)
+        ptr = lambda x: x.ctypes.data if x is not None else 0
+        _lib.check(self.lib.gof_slab_upload(self._handle, int(t.size), *[ptr(x) for x in p], *[ptr(x) for x in v],
+                                            *[ptr(x) for x in a_], ptr(t), ptr(i), self._stream()))
+        torch.cuda.current_stream(self.index).synchronize()
+
+    def download(self):
+        n = int(self.lib.gof_slab_count(self._handle))
+        out = {k: np.empty((3, n), dtype=np.float32) for k in ("pos", "vel", "acc")}
+        ids = np.empty(n, dtype=np.int32)
+        ptrs = [out[k][c].ctypes.data for k in ("pos", "vel", "acc") for c in range(3)]
+        _lib.check(self.lib.gof_slab_download(self._handle, *ptrs, ids.ctypes.data, self._stream()))
+        torch.cuda.current_stream(self.index).synchronize()
+        out["ids"] = ids
+        return out
+
+    def set_parameters(self, parameter_matrix):
+        pm = np.ascontiguousarray(parameter_matrix, dtype=np.float64)
+        _lib.check(self.lib.gof_engine_set_parameters(self._handle, pm.ctypes.data, self._stream()))
+
+    def timing(self, enable: bool):
+        _lib.check(self.lib.gof_engine_timing(self._handle, 1 if enable else 0))
+
+    def force_time(self):
+        ms, k = C.c_float(), C.c_int()
+        _lib.check(self.lib.gof_engine_force_time(self._handle, C.byref(ms), C.byref(k)))
+        return float(ms.value), int(k.value)
+
+    # ---- phases ------------------------------------------------------------------------------
+    def phase_hash(self):
+        out = (C.c_int * 2)()
+        _lib.check(self.lib.gof_slab_phase_hash(self._handle, out, self._stream()))
+        return int(out[0]), int(out[1])
+
+    def mig_send(self, direction: int, n: int) -> torch.Tensor:
+        """direction 0: records going to the slab below, 1: above."""
+        return self._view(self._ptr[direction], n * self.REC, torch.float32)
+
+    def mig_recv(self, source: int, n: int) -> torch.Tensor:
+        """source 0: records coming from the slab below, 1: from above."""
+        return self._view(self._ptr[2 + source], n * self.REC, torch.float32)
+
+    def speed_word(self) -> torch.Tensor:
+        """max |v|^2 of the resident particles as its int32 bit pattern (orders like the float)."""
+        return self._view(self._ptr[7 + int(self.lib.gof_slab_parity(self._handle))], 1, torch.int32)
+
+    def phase_sort(self, n_from_down: int, n_from_up: int, timestep=None):
+        out = (C.c_int * 3)()
+        ts = -1.0 if timestep is None else float(timestep)
+        _lib.check(self.lib.gof_slab_phase_sort(self._handle, int(n_from_down), int(n_from_up), ts, out,
+                                                self._stream()))
+        self.n_live, self.lo_pop, self.hi_pop = int(out[0]), int(out[1]), int(out[2])
+        return self.n_live, self.lo_pop, self.hi_pop
+
+    def _rows(self, first: int, n: int):
+        return (self._view(self._ptr[4] + 16 * first, 4 * n, torch.float32),
+                self._view(self._ptr[5] + 16 * first, 4 * n, torch.float32))
+
+    def _counts(self, layer: int) -> torch.Tensor:
+        return self._view(self._ptr[6] + 4 * layer * self.per_layer, self.per_layer, torch.int32)
+
+    def halo_send(self, direction: int):
+        """Boundary layer handed to the slab below (0) / above (1): positions, velocities, counts."""
+        if direction == 0:
+            pos, vel = self._rows(0, self.lo_pop)
+            return [pos, vel, self._counts(1)]
+        pos, vel = self._rows(self.n_live - self.hi_pop, self.hi_pop)
+        return [pos, vel, self._counts(self.nlz - 2)]
+
+    def halo_recv(self, source: int, n: int, n_before: int = 0):
+        """Where the layer received from the slab below (0) / above (1) goes: behind the owned
+        particles (the upper halo behind the lower one: pass its size as `n_before`)."""
+        pos, vel = self._rows(self.n_live + n_before, n)
+        layer = 0 if source == 0 else self.nlz - 1
+        return [pos, vel, self._counts(layer)]
+
+    def phase_force(self, n_halo_lo: int, n_halo_hi: int):
+        _lib.check(self.lib.gof_slab_phase_force(self._handle, int(n_halo_lo), int(n_halo_hi), self.wrap_mode,
+                                                 self._stream()))
+
+
+@dataclass
+class Transfer:
+    src: int                 # global slab index of the sender
+    dst: int                 # global slab index of the receiver
+    send: object = None      # callable -> list of tensors (evaluated only where src is local)
+    recv: object = None      # callable -> list of tensors (evaluated only where dst is local)
+
+
+class LocalComm:
+    """All slabs live in this process: transfers are device copies."""
+
+    def __init__(self, world_slabs: int):
+        self.world_slabs = world_slabs
+
+    def owner(self, slab: int) -> int:
+        return 0
+
+    def rank(self) -> int:
+        return 0
+
+    def allgather(self, local: dict, width: int) -> dict:
+        return dict(local)
+
+    def allreduce_max(self, words):
+        if len(words) > 1:
+            m = torch.stack([w.reshape(()) for w in words]).max()
+            for w in words:
+                w.fill_(m)
+
+    def exchange(self, transfers):
+        for t in transfers:
+            for s, d in zip(t.send(), t.recv()):
+                if d.numel():
+                    d.copy_(s, non_blocking=True)
+
+
+class DistComm:
+    """One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests).
+    Slab s belongs to rank s * world / world_slabs (normally one slab per rank)."""
+
+    def __init__(self, world_slabs: int, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world_slabs = world_slabs
+        self.world = dist.get_world_size()
+        self._rank = dist.get_rank()
+        self.device = device
+        assert world_slabs % self.world == 0
+        self.per_rank = world_slabs // self.world
+
+    def owner(self, slab: int) -> int:
+        return slab // self.per_rank
+
+    def rank(self) -> int:
+        return self._rank
+
+    def allgather(self, local: dict, width: int) -> dict:
+        """local: {slab: [ints]} for this rank's slabs -> the same for every slab."""
+        mine = torch.zeros(self.per_rank * width, dtype=torch.int64, device=self.device)
+        base = self._rank * self.per_rank
+        flat = []
+        for k in range(self.per_rank):
+            flat += list(local[base + k])
+        mine.copy_(torch.tensor(flat, dtype=torch.int64))
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine)
+        out = {}
+        for r, p in enumerate(parts):
+            vals = p.cpu().tolist()
+            for k in range(self.per_rank):
+                out[r * self.per_rank + k] = vals[k * width:(k + 1) * width]
+        return out
+
+    def allreduce_max(self, words):
+        if len(words) > 1:
+            m = torch.stack([w.reshape(()) for w in words]).max()
+            for w in words:
+                w.fill_(m)
+        self.dist.all_reduce(words[0], op=self.dist.ReduceOp.MAX)
+        for w in words[1:]:
+            w.copy_(words[0])
+
+    def exchange(self, transfers):
+        """Every rank walks the same global list; NCCL matches the send/recv of a pair of
+        ranks in posting order, so the order of the list is the protocol."""
+        ops = []
+        for t in transfers:
+            so, do = self.owner(t.src), self.owner(t.dst)
+            if so == self._rank and do == self._rank:
+                for s, d in zip(t.send(), t.recv()):
+                    if d.numel():
+                        d.copy_(s, non_blocking=True)
+            elif so == self._rank:
+                ops += [self.dist.P2POp(self.dist.isend, s, do) for s in t.send() if s.numel()]
+            elif do == self._rank:
+                ops += [self.dist.P2POp(self.dist.irecv, d, so) for d in t.recv() if d.numel()]
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+class SlabRunner:
+    """Drives the three phases of a step over this process's slabs."""
+
+    def __init__(self, slabs: dict, world_slabs: int, comm):
+        self.slabs = dict(slabs)          # {global slab index: engine}
+        self.world_slabs = int(world_slabs)
+        self.comm = comm
+        self.messages = 0                 # tensors handed to the transport so far (diagnostics)
+
+    def _below(self, s):
+        return (s - 1) % self.world_slabs
+
+    def _above(self, s):
+        return (s + 1) % self.world_slabs
+
+    def step(self, n_steps: int = 1, timestep=None):
+        W = self.world_slabs
+        for _ in range(n_steps):
+            # ---- 1. bin, pack leavers; exchange migration records --------------------------
+            leave = {s: list(e.phase_hash()) for s, e in self.slabs.items()}
+            leave = self.comm.allgather(leave, 2)
+            transfers = []
+            for s in range(W):  # downward records first, then upward: one global order
+                n = leave[s][0]
+                transfers.append(Transfer(s, self._below(s),
+                                          send=lambda s=s, n=n: [self.slabs[s].mig_send(0, n)],
+                                          recv=lambda s=s, n=n: [self.slabs[self._below(s)].mig_recv(1, n)]))
+            for s in range(W):
+                n = leave[s][1]
+                transfers.append(Transfer(s, self._above(s),
+                                          send=lambda s=s, n=n: [self.slabs[s].mig_send(1, n)],
+                                          recv=lambda s=s, n=n: [self.slabs[self._above(s)].mig_recv(0, n)]))
+            self.comm.exchange(transfers)
+            if timestep is None:
+                self.comm.allreduce_max([e.speed_word() for e in self.slabs.values()])
+            # ---- 2. append arrivals, sort; exchange boundary layers ---------------------------
+            pops = {}
+            for s, e in self.slabs.items():
+                from_down = leave[self._below(s)][1]
+                from_up = leave[self._above(s)][0]
+                pops[s] = list(e.phase_sort(from_down, from_up, timestep))
+            pops = self.comm.allgather(pops, 3)
+            transfers = []
+            for s in range(W):  # every slab's bottom layer becomes the upper halo of the slab below
+                n = pops[s][1]
+                d = self._below(s)
+                # the receiver stores the upper halo behind its lower halo (= top layer of ITS lower slab)
+                n_before = pops[self._below(d)][2]
+                transfers.append(Transfer(s, d,
+                                          send=lambda s=s: self.slabs[s].halo_send(0),
+                                          recv=lambda d=d, n=n, nb=n_before: self.slabs[d].halo_recv(1, n, nb)))
+            for s in range(W):  # every slab's top layer becomes the lower halo of the slab above
+                n = pops[s][2]
+                d = self._above(s)
+                transfers.append(Transfer(s, d,
+                                          send=lambda s=s: self.slabs[s].halo_send(1),
+                                          recv=lambda d=d, n=n: self.slabs[d].halo_recv(0, n, 0)))
+            self.comm.exchange(transfers)
+            # ---- 3. forces + integration of the owned particles -----------------------------
+            for s, e in self.slabs.items():
+                e.phase_force(pops[self._below(s)][2], pops[self._above(s)][1])
+            self.messages += 4 * W
+
+    def gather_state(self, num_particles: int):
+        """This process's particles scattered into (3, N) arrays by id (others stay NaN)."""
+        out = {k: np.full((3, num_particles), np.nan, dtype=np.float32) for k in ("pos", "vel", "acc")}
+        owner = np.full(num_particles, -1, dtype=np.int32)
+        for s, e in self.slabs.items():
+            d = e.download()
+            for k in ("pos", "vel", "acc"):
+                out[k][:, d["ids"]] = d[k]
+            owner[d["ids"]] = s
+        out["owner"] = owner
+        return out
+
+
+def assign_to_slabs(pos_z, grid_bin_size_z: float, num_layers: int, layers):
+    """Slab index of every particle from its z bin (host helper for the initial distribution)."""
+    cz = np.minimum(np.floor(np.asarray(pos_z, dtype=np.float64) / grid_bin_size_z).astype(np.int64),
+                    num_layers - 1)
+    slab = np.empty(cz.shape, dtype=np.int32)
+    for s, (lo, hi) in enumerate(layers):
+        slab[(cz >= lo) & (cz < hi)] = s
+    return slab

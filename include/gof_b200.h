@@ -201,6 +201,46 @@ int gof_engine_force_time(gof_engine *e, float *total_ms, int *launches);
 /* The timestep the last step used (synchronises `stream`). */
 int gof_engine_last_timestep(gof_engine *e, float *out, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Slab decomposition (multi-GPU).  The periodic box is cut along z into slabs of
+ * whole bin layers; one engine (one GPU, one process) owns the layers
+ * [layer_lo, layer_hi) plus one halo layer on either side.  The host drives three
+ * phases per step and moves the buffers between neighbouring slabs with NCCL
+ * send/recv (game_of_flies_b200/slab.py); every phase that produces sizes the host
+ * needs synchronises `stream` and returns them.
+ *
+ *   1. gof_slab_phase_hash : bin resident particles, pack the ones that left the slab
+ *                            -> exchange migration records with the two neighbours
+ *   2. gof_slab_phase_sort : append arrivals, counting sort, step1 kick
+ *                            -> exchange boundary layers (positions, velocities, counts)
+ *   3. gof_slab_phase_force: halo cell table, neighbour forces + integrator (owned only)
+ *
+ * With an adaptive timestep the maximum squared speed (pointer 7 or 8 of
+ * gof_slab_pointers, chosen by gof_slab_parity) is all-reduced (MAX, as int32 bit
+ * patterns) between phases 1 and 2.  Results are bit-identical to the single-GPU engine.
+ * ---------------------------------------------------------------------- */
+int gof_slab_create(gof_engine **out, int device, int capacity, int num_types, const gof_grid *grid,
+                    const double *parameter_matrix_host, int layer_lo, int layer_hi,
+                    int migrate_capacity, int halo_capacity);
+/* Upload this slab's particles with their global ids. */
+int gof_slab_upload(gof_engine *e, int num_particles, const float *pos_x_any, const float *pos_y_any,
+                    const float *pos_z_any, const float *vel_x_any, const float *vel_y_any,
+                    const float *vel_z_any, const float *acc_x_any, const float *acc_y_any,
+                    const float *acc_z_any, const int32_t *types_any, const int32_t *ids_any, void *stream);
+/* ptrs[0..9]: migration send down / send up / recv from below / recv from above (records of
+ * three float4), snapshot positions, snapshot velocities (float4 each, cell order), cell counts
+ * (int32), the two max-squared-speed slots (uint32 bit patterns), cell starts (int32). */
+int gof_slab_pointers(gof_engine *e, void **ptrs, int n_ptrs);
+int gof_slab_phase_hash(gof_engine *e, int *out_counts2, void *stream);
+int gof_slab_phase_sort(gof_engine *e, int n_from_down, int n_from_up, float timestep,
+                        int *out_counts3, void *stream);
+int gof_slab_phase_force(gof_engine *e, int n_halo_lo, int n_halo_hi, int wrap_mode, void *stream);
+int gof_slab_parity(const gof_engine *e);
+int gof_slab_count(const gof_engine *e);
+int gof_slab_download(gof_engine *e, float *pos_x_any, float *pos_y_any, float *pos_z_any,
+                      float *vel_x_any, float *vel_y_any, float *vel_z_any, float *acc_x_any,
+                      float *acc_y_any, float *acc_z_any, int32_t *ids_any, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
