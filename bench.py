@@ -231,11 +231,11 @@ def workload_config(args, hs, n_total, note=None):
         "workload": f"{kind.capitalize()} {dims}D, {species} species, N={n_total}, periodic box "
                     f"{tuple(round(float(x), 2) for x in hs['box'])}, density {hs['density']:.4g}, "
                     f"r_max {float(hs['r_max']):.3f}, uniform random start, adaptive timestep",
-        "particles_per_gpu": int(n_total // max(args.gpus, 1)),
+        "particles_per_gpu": int(n_total // max(int(os.environ.get("WORLD_SIZE", "1")), 1)),
         "bins": [int(hs["num_bin_x"]), int(hs["num_bin_y"]), int(hs["num_bin_z"])],
         "wrap_mode": "reference",
-        "cache": "state (5 x 16 B x N) exceeds L2 for N >= 2M; at 1M the 80 MB of state arrays are "
-                 "streamed once per step between other kernels' 60 MB of scratch: inputs larger than L2",
+        "cache": ("L2 flushed between timed steps (256 MiB overwrite outside the per-step event pairs)"
+                  if getattr(args, "flush_l2", True) else "no L2 flush: per-step working set ~100 MB at N = 1M"),
     }
     if note:
         cfg["note"] = note
@@ -255,6 +255,9 @@ def main():
     ap.add_argument("--seed", type=int, default=434)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false",
+                    help="do not overwrite a 256 MiB buffer between timed steps")
+    ap.add_argument("--packed", action="store_true", help="use the packed two-homes-per-lane Clusters kernel")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -283,42 +286,105 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    # ---- workload: every rank owns `--particles` particles (weak scaling) ------------------
-    n = args.particles
-    hs = build_workload(args.workload, n, args.seed + rank, args.density)
-    init = hs["init"]
-    pin = lambda a, dt=np.float32: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory()
-    h_pos = [pin(init[k]) for k in ("pos_x", "pos_y", "pos_z")]
-    h_vel = [pin(init[k]) for k in ("vel_x", "vel_y", "vel_z")]
-    h_acc = [pin(init[k]) for k in ("acc_x", "acc_y", "acc_z")]
-    h_types = pin(hs["particle_type_index_array"], np.int32)
-    o_pos = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
-    o_vel = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
-    o_acc = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
-
-    eng = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), device=device)
-    eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
     lib = _lib.load()
+    n = args.particles
+    cand = None
+    if world == 1:
+        # ---- one GPU: the resident engine on the whole periodic box -------------------------
+        hs = build_workload(args.workload, n, args.seed, args.density)
+        init = hs["init"]
+        pin = lambda a, dt=np.float32: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory()
+        h_pos = [pin(init[k]) for k in ("pos_x", "pos_y", "pos_z")]
+        h_vel = [pin(init[k]) for k in ("vel_x", "vel_y", "vel_z")]
+        h_acc = [pin(init[k]) for k in ("acc_x", "acc_y", "acc_z")]
+        h_types = pin(hs["particle_type_index_array"], np.int32)
+        o_pos = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
+        o_vel = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
+        o_acc = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
+        eng = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), device=device,
+                             packed=args.packed)
+        eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
+        step = lambda k: eng.step(k)
+
+        def e2e_step():
+            nonlocal h_pos, h_vel, h_acc, o_pos, o_vel, o_acc
+            eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
+            eng.step(1)
+            eng.download_into(pos=o_pos, vel=o_vel, acc=o_acc)
+            torch.cuda.current_stream(device).synchronize()
+            # the next step of a host-driven loop starts from what came back
+            h_pos, o_pos = o_pos, h_pos
+            h_vel, o_vel = o_vel, h_vel
+            h_acc, o_acc = o_acc, h_acc
+    else:
+        # ---- several GPUs: z-slab decomposition, one slab per rank, weak scaling -----------------
+        # the box of the one-GPU workload stacked `world` times along z; every rank starts with
+        # `n` particles uniform in its own slab
+        from game_of_flies_b200.slab import DistComm, SlabEngine, SlabRunner, split_layers
+        hs = build_workload(args.workload, 1000, args.seed, args.density)  # species parameters only
+        kind, species, dims = WORKLOADS[args.workload]
+        if dims != 3:
+            raise SystemExit("the slab decomposition needs a 3D workload")
+        rho = hs["density"]
+        side = float((n / rho) ** (1.0 / 3.0))
+        limits = np.array([side, side, side * world])
+        hs["limits"], hs["box"] = limits, tuple(limits)
+        grid = _lib.make_grid(limits, float(hs["r_max"]))
+        hs["num_bin_x"], hs["num_bin_y"], hs["num_bin_z"] = grid.num_bin_x, grid.num_bin_y, grid.num_bin_z
+        layers = split_layers(int(grid.num_bin_z), world)
+        lo, hi = layers[rank]
+        rng = np.random.default_rng(args.seed + rank)
+        pos = rng.random((3, n))
+        pos[0] *= side
+        pos[1] *= side
+        pos[2] = (lo + pos[2] * (hi - lo)) * grid.bin_size_z
+        pos = pos.astype(np.float32)
+        types = np.repeat(np.arange(species, dtype=np.int32), -(-n // species))[:n]
+        ids = np.arange(n, dtype=np.int32) + rank * n
+        zeros = np.zeros((3, n), dtype=np.float32)
+        eng = SlabEngine(hs["parameter_matrix"], limits, float(hs["r_max"]), lo, hi, capacity=int(1.3 * n) + 8192,
+                         device=device)
+        eng.upload(pos, types, ids, vel=zeros, acc=zeros)
+        runner = SlabRunner({rank: eng}, world, DistComm(world, device=device))
+        step = lambda k: runner.step(k)
+        state = {"pos": pos, "vel": zeros, "acc": zeros, "types": types, "ids": ids}
+
+        def e2e_step():
+            eng.upload(state["pos"], state["types"], state["ids"], vel=state["vel"], acc=state["acc"])
+            runner.step(1)
+            d = eng.download()
+            state["pos"], state["vel"], state["acc"], state["ids"] = d["pos"], d["vel"], d["acc"], d["ids"]
+            # types travel with the particles: recover them from the ids (species are id ranges per rank)
+            state["types"] = types[(d["ids"] % n)]
 
     # ---- device-resident throughput ------------------------------------------------------------
-    eng.step(args.warmup)
+    step(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     eng.timing(True)
     lib.gof_reset_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Every timed step starts with a cold L2: a 256 MiB buffer (2x the 126 MB L2) is overwritten
+    # between steps, outside the per-step event pairs, because the per-step working set at
+    # N = 1M (~100 MB) would otherwise stay L2-resident from one step to the next.
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if args.flush_l2 else None
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
-    ev0.record()
-    eng.step(args.steps)
-    ev1.record()
+    for k in range(args.steps):
+        if flush is not None:
+            flush.fill_(k & 0xFF)
+        starts[k].record()
+        step(1)
+        stops[k].record()
     barrier()
     launches = int(lib.gof_launch_count())
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = float(sum(a.elapsed_time(b) for a, b in zip(starts, stops)))
     force_ms, force_launches = eng.force_time()
     eng.timing(False)
     clocks = sampler.stop()
-    cand = eng.candidate_pairs()
+    if world == 1:
+        cand = eng.candidate_pairs()
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,18 +393,11 @@ def main():
     value = world * n * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the public API with host buffers ------------------------------
-    # every step: pinned host state -> device, one core_step, full state back to pinned host
+    # every step: host state -> device, one core_step, full state back to the host
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
-        eng.step(1)
-        eng.download_into(pos=o_pos, vel=o_vel, acc=o_acc)
-        torch.cuda.current_stream(device).synchronize()
-        # the next step of a host-driven loop starts from what came back
-        h_pos, o_pos = o_pos, h_pos
-        h_vel, o_vel = o_vel, h_vel
-        h_acc, o_acc = o_acc, h_acc
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
@@ -346,8 +405,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = world * n * args.e2e_steps / e2e_s
-    h2d = n * (9 * 4 + 4)
-    d2h = n * 9 * 4
+    h2d = n * (9 * 4 + 4) + (n * 4 if world > 1 else 0)
+    d2h = n * 9 * 4 + (n * 4 if world > 1 else 0)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -362,8 +421,8 @@ def main():
             "avg_launch_ms": force_avg_ms, "launches_timed": force_launches,
             "share_of_step": force_ms / ms_total if ms_total > 0 else None,
             # why the HBM fraction is what it is: the kernel is fp32-issue bound on pair tests
-            "candidate_pairs_per_particle": cand / n,
-            "pair_tests_per_s": cand / (force_avg_ms * 1e-3),
+            "candidate_pairs_per_particle": (cand / n) if cand is not None else None,
+            "pair_tests_per_s": (cand / (force_avg_ms * 1e-3)) if cand is not None else None,
         }
         line = {
             "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s",
@@ -372,12 +431,14 @@ def main():
             "data": "synthetic",
             "config": workload_config(args, hs, world * n,
                                       note=None if world == 1 else
-                                      "one independent periodic box per rank (replicas)"),
+                                      f"one periodic box cut into {world} z-slabs (one per GPU); halo layers and "
+                                      "migrating particles move with NCCL send/recv, message sizes with two small "
+                                      "all-gathers per step, the adaptive timestep with a one-word MAX all-reduce"),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps,
-                    "what": "gof_engine_upload(pinned host pos/vel/acc/types) + gof_engine_step + "
-                            "gof_engine_download(pinned host pos/vel/acc), synchronised every step"},
+                    "what": "upload(host pos/vel/acc/types) + one core_step + download(host pos/vel/acc) through "
+                            "the C ABI, synchronised every step"},
             "gpu_launches": launches,
             "roofline": roofline,
         }

@@ -711,7 +711,7 @@ struct gof_engine {
     int halo_capacity = 0;  // halo particles per side
     float4 *mig_send[2] = {nullptr, nullptr};  // [0] down, [1] up
     float4 *mig_recv[2] = {nullptr, nullptr};  // [0] from the slab below, [1] from above
-    int* counters = nullptr;                   // MigrateOut counters (4 ints)
+    int* counters = nullptr;                   // [0..2] leavers down / up / error, [4..7] sort results
     int n_slots = 0;        // resident slots before the sort (live + dead + arrivals)
     int n_halo[2] = {0, 0};
 
@@ -767,7 +767,7 @@ static size_t engine_layout(gof_engine* e, char* base)
             e->mig_send[d] = (float4*)take((size_t)e->mig_capacity * 3 * sizeof(float4));
             e->mig_recv[d] = (float4*)take((size_t)e->mig_capacity * 3 * sizeof(float4));
         }
-        e->counters = (int*)take(4 * sizeof(int));
+        e->counters = (int*)take(8 * sizeof(int));
     }
     return o;
 }
@@ -1189,7 +1189,7 @@ extern "C" int gof_slab_upload(gof_engine* e, int n, const float* px, const floa
 extern "C" int gof_slab_pointers(gof_engine* e, void** ptrs, int n_ptrs)
 {
     if (int rc = slab_ready(e, false)) return rc;
-    if (!ptrs || n_ptrs < 10) return fail(GOF_E_INVALID, "gof_slab_pointers: need room for 10 pointers");
+    if (!ptrs || n_ptrs < 11) return fail(GOF_E_INVALID, "gof_slab_pointers: need room for 11 pointers");
     ptrs[0] = e->mig_send[0];
     ptrs[1] = e->mig_send[1];
     ptrs[2] = e->mig_recv[0];
@@ -1200,46 +1200,75 @@ extern "C" int gof_slab_pointers(gof_engine* e, void** ptrs, int n_ptrs)
     ptrs[7] = &e->scalars->max_sq_speed_bits[0];
     ptrs[8] = &e->scalars->max_sq_speed_bits[1];
     ptrs[9] = e->start;
+    ptrs[10] = e->counters;
     return 0;
 }
 
-/* Phase 1: bin the resident particles; the ones that left the slab are packed into the
- * send buffers.  Synchronises `stream`; out_counts = {going down, going up}. */
-extern "C" int gof_slab_phase_hash(gof_engine* e, int* out_counts, void* stream)
+namespace gof {
+// {live particles, population of the bottom owned layer, of the top owned layer, error flag}
+__global__ void k_slab_counts(const int* __restrict__ start, const int* __restrict__ counters_in,
+                              int* __restrict__ out, int num_cells, int per_layer, int top)
+{
+    out[0] = start[num_cells];
+    out[1] = start[2 * per_layer] - start[per_layer];
+    out[2] = start[(top + 1) * per_layer] - start[top * per_layer];
+    out[3] = counters_in[2];
+}
+}  // namespace gof
+
+/* Phase 1 (asynchronous): bin the resident particles; the ones that left the slab are packed
+ * into the send buffers.  Afterwards counters[0..2] (pointer 10 of gof_slab_pointers) hold
+ * {going down, going up, error flag} on the device; the host all-gathers them. */
+extern "C" int gof_slab_phase_hash_async(gof_engine* e, void* stream)
 {
     if (int rc = slab_ready(e, true)) return rc;
-    if (!out_counts) return fail(GOF_E_INVALID, "gof_slab_phase_hash: null output");
     cudaStream_t st = (cudaStream_t)stream;
     const Geometry& g = e->geom;
     GOF_CUDA(cudaMemsetAsync(e->count, 0, (size_t)(g.num_cells + 2) * sizeof(int), st));
-    GOF_CUDA(cudaMemsetAsync(e->counters, 0, 4 * sizeof(int), st));
+    GOF_CUDA(cudaMemsetAsync(e->counters, 0, 8 * sizeof(int), st));
     if (e->n > 0) {
         MigrateOut mig{e->mig_send[0], e->mig_send[1], e->counters, e->mig_capacity};
         GOF_LAUNCH(k_hash_count<false>, cdiv(e->n, kBinThreads), kBinThreads, 0, st, e->posw[0], e->veli[0], e->acc,
                    (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, e->n, g, e->cell_of, e->off,
                    e->count, mig);
     }
-    int h[4] = {0, 0, 0, 0};
-    GOF_CUDA(cudaMemcpyAsync(h, e->counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    GOF_CUDA(cudaStreamSynchronize(st));
-    if (h[2] == 1) return fail(GOF_E_STATE, "slab: a particle moved more than one layer in a step");
-    if (h[2] == 2 || h[0] > e->mig_capacity || h[1] > e->mig_capacity)
-        return fail(GOF_E_NOMEM, "slab: migration buffer overflow (raise migrate_capacity)");
-    out_counts[0] = h[0];
-    out_counts[1] = h[1];
     e->n_slots = e->n;
     return 0;
 }
 
-/* Phase 2: append the arrivals (already received into the recv buffers), bin them, sort
- * everything by cell and kick the velocities.  The maximum squared speed must have been
- * all-reduced over the slabs before this call when the timestep is adaptive.
- * Synchronises; out_counts = {live particles, population of the bottom owned layer, of the top one}. */
-extern "C" int gof_slab_phase_sort(gof_engine* e, int n_from_down, int n_from_up, float timestep,
-                                   int* out_counts, void* stream)
+static int slab_check_hash(gof_engine* e, const int* h)
+{
+    if (h[2] == 1) return fail(GOF_E_STATE, "slab: a particle moved more than one layer in a step");
+    if (h[2] == 2 || h[0] > e->mig_capacity || h[1] > e->mig_capacity)
+        return fail(GOF_E_NOMEM, "slab: migration buffer overflow (raise migrate_capacity)");
+    return 0;
+}
+
+/* Phase 1, synchronous form: out_counts = {going down, going up}. */
+extern "C" int gof_slab_phase_hash(gof_engine* e, int* out_counts, void* stream)
+{
+    if (!out_counts) return fail(GOF_E_INVALID, "gof_slab_phase_hash: null output");
+    if (int rc = gof_slab_phase_hash_async(e, stream)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int h[4] = {0, 0, 0, 0};
+    GOF_CUDA(cudaMemcpyAsync(h, e->counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GOF_CUDA(cudaStreamSynchronize(st));
+    if (int rc = slab_check_hash(e, h)) return rc;
+    out_counts[0] = h[0];
+    out_counts[1] = h[1];
+    return 0;
+}
+
+/* Phase 2 (asynchronous): append the arrivals (already received into the recv buffers), bin
+ * them, sort everything by cell and kick the velocities.  The maximum squared speed must have
+ * been all-reduced over the slabs before this call when the timestep is adaptive.  Afterwards
+ * counters[4..7] hold {live particles, population of the bottom owned layer, of the top one,
+ * error flag}; the host all-gathers them and reports them back with gof_slab_commit. */
+extern "C" int gof_slab_phase_sort_async(gof_engine* e, int n_from_down, int n_from_up, float timestep,
+                                         void* stream)
 {
     if (int rc = slab_ready(e, true)) return rc;
-    if (!out_counts || n_from_down < 0 || n_from_up < 0) return fail(GOF_E_INVALID, "gof_slab_phase_sort: bad arguments");
+    if (n_from_down < 0 || n_from_up < 0) return fail(GOF_E_INVALID, "gof_slab_phase_sort: bad arguments");
     if (n_from_down > e->mig_capacity || n_from_up > e->mig_capacity)
         return fail(GOF_E_NOMEM, "slab: more arrivals than migrate_capacity");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1265,25 +1294,39 @@ extern "C" int gof_slab_phase_sort(gof_engine* e, int n_from_down, int n_from_up
                    e->count, e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1],
                    e->cell_sorted, (float4*)nullptr, (float4*)nullptr, e->scalars, 1);
     }
-    // live count and the populations of the two owned boundary layers, from the start table
-    const int per_layer = g.nbx * g.nby;
-    const int top = g.nlz - 2;  // local index of the top owned layer
-    int h[5];
-    const int idx[4] = {g.num_cells, 2 * per_layer, top * per_layer, (top + 1) * per_layer};
-    for (int k = 0; k < 4; ++k)
-        GOF_CUDA(cudaMemcpyAsync(&h[k], e->start + idx[k], sizeof(int), cudaMemcpyDeviceToHost, st));
-    GOF_CUDA(cudaMemcpyAsync(&h[4], &e->counters[2], sizeof(int), cudaMemcpyDeviceToHost, st));
-    GOF_CUDA(cudaStreamSynchronize(st));
-    if (h[4] != 0) return fail(GOF_E_STATE, "slab: an arriving particle does not belong to this slab");
-    const int n_live = h[0];
-    out_counts[0] = n_live;
-    out_counts[1] = (top >= 2) ? h[1] : n_live;           // bottom owned layer = local layer 1 (starts at 0)
-    out_counts[2] = (top >= 2) ? h[3] - h[2] : n_live;    // top owned layer
-    if (out_counts[1] > e->halo_capacity || out_counts[2] > e->halo_capacity)
-        return fail(GOF_E_NOMEM, "slab: boundary layer larger than halo_capacity");
-    e->n = n_live;
+    GOF_LAUNCH(k_slab_counts, 1, 1, 0, st, e->start, e->counters, e->counters + 4, g.num_cells, g.nbx * g.nby,
+               g.nlz - 2);
     e->binned = true;
     e->binned_packed = false;
+    return 0;
+}
+
+/* The host's copy of counters[4..7] after phase 2 (it needs them for the halo messages anyway). */
+extern "C" int gof_slab_commit(gof_engine* e, int n_live, int lo_pop, int hi_pop, int error)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    if (error != 0) return fail(GOF_E_STATE, "slab: an arriving particle does not belong to this slab");
+    if (n_live < 0 || n_live > e->capacity) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
+    if (lo_pop > e->halo_capacity || hi_pop > e->halo_capacity)
+        return fail(GOF_E_NOMEM, "slab: boundary layer larger than halo_capacity");
+    e->n = n_live;
+    return 0;
+}
+
+/* Phase 2, synchronous form: out_counts = {live, bottom layer population, top layer population}. */
+extern "C" int gof_slab_phase_sort(gof_engine* e, int n_from_down, int n_from_up, float timestep,
+                                   int* out_counts, void* stream)
+{
+    if (!out_counts) return fail(GOF_E_INVALID, "gof_slab_phase_sort: null output");
+    if (int rc = gof_slab_phase_sort_async(e, n_from_down, n_from_up, timestep, stream)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int h[4];
+    GOF_CUDA(cudaMemcpyAsync(h, e->counters + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GOF_CUDA(cudaStreamSynchronize(st));
+    if (int rc = gof_slab_commit(e, h[0], h[1], h[2], h[3])) return rc;
+    out_counts[0] = h[0];
+    out_counts[1] = h[1];
+    out_counts[2] = h[2];
     return 0;
 }
 

@@ -56,6 +56,7 @@ class SlabEngine:
         self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         pm = np.ascontiguousarray(parameter_matrix, dtype=np.float64)
         self.num_types = int(pm.shape[1])
+        self.has_boids = bool(np.any(pm[-1] == 1))  # Boids alignment reads the neighbours' velocities
         self.grid = _lib.make_grid(limits, r_max)
         self.layer_lo, self.layer_hi = int(layer_lo), int(layer_hi)
         self.nlz = self.layer_hi - self.layer_lo + 2
@@ -75,8 +76,8 @@ class SlabEngine:
             self.arena = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
         self._arena_ptr = (self.arena.data_ptr() + 255) // 256 * 256
         _lib.check(self.lib.gof_engine_bind_arena(self._handle, self._arena_ptr, nbytes))
-        ptrs = (C.c_void_p * 10)()
-        _lib.check(self.lib.gof_slab_pointers(self._handle, ptrs, 10))
+        ptrs = (C.c_void_p * 11)()
+        _lib.check(self.lib.gof_slab_pointers(self._handle, ptrs, 11))
         self._ptr = [int(p or 0) for p in ptrs]
         self.n_live = 0
         self.lo_pop = self.hi_pop = 0
@@ -139,10 +140,21 @@ class SlabEngine:
         return float(ms.value), int(k.value)
 
     # ---- phases ------------------------------------------------------------------------------
+    # Phases 1 and 2 only enqueue work.  Their results (message sizes) stay in four device
+    # words that the runner all-gathers straight from device memory: one host synchronisation
+    # per phase for all slabs together.
     def phase_hash(self):
-        out = (C.c_int * 2)()
-        _lib.check(self.lib.gof_slab_phase_hash(self._handle, out, self._stream()))
-        return int(out[0]), int(out[1])
+        _lib.check(self.lib.gof_slab_phase_hash_async(self._handle, self._stream()))
+
+    def hash_words(self) -> torch.Tensor:
+        """int32[4] on the device after phase_hash: going down, going up, error flag, 0."""
+        return self._view(self._ptr[10], 4, torch.int32)
+
+    def check_hash(self, words):
+        if words[2] == 1:
+            raise _lib.GofError(_lib.E_STATE, "slab: a particle moved more than one layer in a step")
+        if words[2] == 2 or max(words[0], words[1]) > self.migrate_capacity:
+            raise _lib.GofError(_lib.E_NOMEM, "slab: migration buffer overflow (raise migrate_capacity)")
 
     def mig_send(self, direction: int, n: int) -> torch.Tensor:
         """direction 0: records going to the slab below, 1: above."""
@@ -157,12 +169,17 @@ class SlabEngine:
         return self._view(self._ptr[7 + int(self.lib.gof_slab_parity(self._handle))], 1, torch.int32)
 
     def phase_sort(self, n_from_down: int, n_from_up: int, timestep=None):
-        out = (C.c_int * 3)()
         ts = -1.0 if timestep is None else float(timestep)
-        _lib.check(self.lib.gof_slab_phase_sort(self._handle, int(n_from_down), int(n_from_up), ts, out,
-                                                self._stream()))
-        self.n_live, self.lo_pop, self.hi_pop = int(out[0]), int(out[1]), int(out[2])
-        return self.n_live, self.lo_pop, self.hi_pop
+        _lib.check(self.lib.gof_slab_phase_sort_async(self._handle, int(n_from_down), int(n_from_up), ts,
+                                                      self._stream()))
+
+    def sort_words(self) -> torch.Tensor:
+        """int32[4] on the device after phase_sort: live, bottom layer, top layer population, error flag."""
+        return self._view(self._ptr[10] + 16, 4, torch.int32)
+
+    def commit(self, words):
+        _lib.check(self.lib.gof_slab_commit(self._handle, int(words[0]), int(words[1]), int(words[2]), int(words[3])))
+        self.n_live, self.lo_pop, self.hi_pop = int(words[0]), int(words[1]), int(words[2])
 
     def _rows(self, first: int, n: int):
         return (self._view(self._ptr[4] + 16 * first, 4 * n, torch.float32),
@@ -171,20 +188,21 @@ class SlabEngine:
     def _counts(self, layer: int) -> torch.Tensor:
         return self._view(self._ptr[6] + 4 * layer * self.per_layer, self.per_layer, torch.int32)
 
+    def _layer_msgs(self, first: int, n: int, layer: int):
+        pos, vel = self._rows(first, n)
+        return [pos, vel, self._counts(layer)] if self.has_boids else [pos, self._counts(layer)]
+
     def halo_send(self, direction: int):
-        """Boundary layer handed to the slab below (0) / above (1): positions, velocities, counts."""
+        """Boundary layer handed to the slab below (0) / above (1): cell-ordered positions (and
+        velocities when some species pair is of the Boids kind) plus the per-cell counts."""
         if direction == 0:
-            pos, vel = self._rows(0, self.lo_pop)
-            return [pos, vel, self._counts(1)]
-        pos, vel = self._rows(self.n_live - self.hi_pop, self.hi_pop)
-        return [pos, vel, self._counts(self.nlz - 2)]
+            return self._layer_msgs(0, self.lo_pop, 1)
+        return self._layer_msgs(self.n_live - self.hi_pop, self.hi_pop, self.nlz - 2)
 
     def halo_recv(self, source: int, n: int, n_before: int = 0):
         """Where the layer received from the slab below (0) / above (1) goes: behind the owned
         particles (the upper halo behind the lower one: pass its size as `n_before`)."""
-        pos, vel = self._rows(self.n_live + n_before, n)
-        layer = 0 if source == 0 else self.nlz - 1
-        return [pos, vel, self._counts(layer)]
+        return self._layer_msgs(self.n_live + n_before, n, 0 if source == 0 else self.nlz - 1)
 
     def phase_force(self, n_halo_lo: int, n_halo_hi: int):
         _lib.check(self.lib.gof_slab_phase_force(self._handle, int(n_halo_lo), int(n_halo_hi), self.wrap_mode,
@@ -211,8 +229,11 @@ class LocalComm:
     def rank(self) -> int:
         return 0
 
-    def allgather(self, local: dict, width: int) -> dict:
-        return dict(local)
+    def gather_words(self, local: dict) -> dict:
+        """{slab: int32[4] tensor} -> {slab: [4 ints]}; one synchronisation for all of them."""
+        keys = sorted(local)
+        vals = torch.stack([local[k] for k in keys]).cpu().tolist()
+        return dict(zip(keys, vals))
 
     def allreduce_max(self, words):
         if len(words) > 1:
@@ -247,22 +268,20 @@ class DistComm:
     def rank(self) -> int:
         return self._rank
 
-    def allgather(self, local: dict, width: int) -> dict:
-        """local: {slab: [ints]} for this rank's slabs -> the same for every slab."""
-        mine = torch.zeros(self.per_rank * width, dtype=torch.int64, device=self.device)
+    def gather_words(self, local: dict) -> dict:
+        """{slab: int32[4] tensor} of this rank's slabs -> {slab: [4 ints]} for every slab.
+        The words are all-gathered from where the kernels left them (device memory under
+        NCCL), then read back once."""
         base = self._rank * self.per_rank
-        flat = []
-        for k in range(self.per_rank):
-            flat += list(local[base + k])
-        mine.copy_(torch.tensor(flat, dtype=torch.int64))
-        parts = [torch.empty_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(parts, mine)
-        out = {}
-        for r, p in enumerate(parts):
-            vals = p.cpu().tolist()
-            for k in range(self.per_rank):
-                out[r * self.per_rank + k] = vals[k * width:(k + 1) * width]
-        return out
+        mine = torch.stack([local[base + k] for k in range(self.per_rank)]).reshape(-1).contiguous()
+        out = torch.empty(self.world * mine.numel(), dtype=mine.dtype, device=mine.device)
+        if self.dist.get_backend() == "gloo":
+            parts = list(out.chunk(self.world))
+            self.dist.all_gather(parts, mine)
+        else:
+            self.dist.all_gather_into_tensor(out, mine)
+        vals = out.cpu().reshape(self.world_slabs, 4).tolist()
+        return {s: vals[s] for s in range(self.world_slabs)}
 
     def allreduce_max(self, words):
         if len(words) > 1:
@@ -311,8 +330,11 @@ class SlabRunner:
         W = self.world_slabs
         for _ in range(n_steps):
             # ---- 1. bin, pack leavers; exchange migration records --------------------------
-            leave = {s: list(e.phase_hash()) for s, e in self.slabs.items()}
-            leave = self.comm.allgather(leave, 2)
+            for e in self.slabs.values():
+                e.phase_hash()
+            leave = self.comm.gather_words({s: e.hash_words() for s, e in self.slabs.items()})
+            for s, e in self.slabs.items():
+                e.check_hash(leave[s])
             transfers = []
             for s in range(W):  # downward records first, then upward: one global order
                 n = leave[s][0]
@@ -328,12 +350,11 @@ class SlabRunner:
             if timestep is None:
                 self.comm.allreduce_max([e.speed_word() for e in self.slabs.values()])
             # ---- 2. append arrivals, sort; exchange boundary layers ---------------------------
-            pops = {}
             for s, e in self.slabs.items():
-                from_down = leave[self._below(s)][1]
-                from_up = leave[self._above(s)][0]
-                pops[s] = list(e.phase_sort(from_down, from_up, timestep))
-            pops = self.comm.allgather(pops, 3)
+                e.phase_sort(leave[self._below(s)][1], leave[self._above(s)][0], timestep)
+            pops = self.comm.gather_words({s: e.sort_words() for s, e in self.slabs.items()})
+            for s, e in self.slabs.items():
+                e.commit(pops[s])
             transfers = []
             for s in range(W):  # every slab's bottom layer becomes the upper halo of the slab below
                 n = pops[s][1]

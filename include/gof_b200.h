@@ -227,13 +227,20 @@ int gof_slab_upload(gof_engine *e, int num_particles, const float *pos_x_any, co
                     const float *pos_z_any, const float *vel_x_any, const float *vel_y_any,
                     const float *vel_z_any, const float *acc_x_any, const float *acc_y_any,
                     const float *acc_z_any, const int32_t *types_any, const int32_t *ids_any, void *stream);
-/* ptrs[0..9]: migration send down / send up / recv from below / recv from above (records of
+/* ptrs[0..10]: migration send down / send up / recv from below / recv from above (records of
  * three float4), snapshot positions, snapshot velocities (float4 each, cell order), cell counts
- * (int32), the two max-squared-speed slots (uint32 bit patterns), cell starts (int32). */
+ * (int32), the two max-squared-speed slots (uint32 bit patterns), cell starts (int32), the 8 counter words (int32). */
 int gof_slab_pointers(gof_engine *e, void **ptrs, int n_ptrs);
 int gof_slab_phase_hash(gof_engine *e, int *out_counts2, void *stream);
 int gof_slab_phase_sort(gof_engine *e, int n_from_down, int n_from_up, float timestep,
                         int *out_counts3, void *stream);
+/* Asynchronous forms: nothing is copied to the host.  The results stay in the device words
+ * of pointer 10 ([0..2] = going down / going up / error after phase 1, [4..7] = live / bottom
+ * layer / top layer / error after phase 2) so that the host can all-gather them straight from
+ * device memory and synchronise once; it then reports phase 2's words with gof_slab_commit. */
+int gof_slab_phase_hash_async(gof_engine *e, void *stream);
+int gof_slab_phase_sort_async(gof_engine *e, int n_from_down, int n_from_up, float timestep, void *stream);
+int gof_slab_commit(gof_engine *e, int n_live, int lo_pop, int hi_pop, int error);
 int gof_slab_phase_force(gof_engine *e, int n_halo_lo, int n_halo_hi, int wrap_mode, void *stream);
 int gof_slab_parity(const gof_engine *e);
 int gof_slab_count(const gof_engine *e);

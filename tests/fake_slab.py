@@ -29,6 +29,7 @@ class FakeSlabEngine:
         self._send = [None, None]
         self._recv = [None, None]
         self._halo = [None, None]
+        self._words = torch.zeros(4, dtype=torch.int32)
         self.n_live = self.lo_pop = self.hi_pop = 0
 
     # ---- state ----
@@ -68,7 +69,19 @@ class FakeSlabEngine:
         keep = ~(down | up)
         self.pos, self.vel, self.acc = self.pos[:, keep], self.vel[:, keep], self.acc[:, keep]
         self.types, self.ids = self.types[keep], self.ids[keep]
-        return int(down.sum()), int(up.sum())
+        self._words = torch.tensor([int(down.sum()), int(up.sum()), 0, 0], dtype=torch.int32)
+
+    def hash_words(self):
+        return self._words
+
+    def check_hash(self, words):
+        assert words[2] == 0
+
+    def sort_words(self):
+        return self._words
+
+    def commit(self, words):
+        assert words[3] == 0 and (self.n_live, self.lo_pop, self.hi_pop) == tuple(words[:3])
 
     def mig_send(self, direction, n):
         assert self._send[direction].numel() == n * 12
@@ -109,7 +122,7 @@ class FakeSlabEngine:
         self.n_live = len(self.ids)
         self.lo_pop = int((lz == 1).sum())
         self.hi_pop = int((lz == self.nlz - 2).sum())
-        return self.n_live, self.lo_pop, self.hi_pop
+        self._words = torch.tensor([self.n_live, self.lo_pop, self.hi_pop, 0], dtype=torch.int32)
 
     def _layer(self, first, n, layer):
         pos = np.zeros((n, 4)); pos[:, :3] = self.pos[:, first:first + n].T; pos[:, 3] = self.types[first:first + n]
