@@ -39,7 +39,7 @@ OUT_DIR = os.path.dirname(os.path.abspath(__file__))
 # name: (clus_types, boid_types, seed, limits, steps, timestep)
 CASES = {
     # BASELINE.json configs[0]: Clusters 2D, 3 species, N=2,000, periodic box
-    "clusters2d_3sp_n2000": ([700, 700, 600], [0], 4, (100, 100, 0), 2, None),
+    "clusters2d_3sp_n2000": ([700, 700, 600], [0], 4, (100, 100, 0), 1, None),
     "clusters2d_3sp_n300": ([100, 100, 100], [0], 434, (100, 100, 0), 6, None),
     "clusters2d_fixed_dt": ([120, 90], [0], 35, (60, 80, 0), 4, 0.02),
     "clusters3d_5sp_n400": ([80, 80, 80, 80, 80], [0], 10, (40, 40, 40), 4, None),
