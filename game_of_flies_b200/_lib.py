@@ -78,12 +78,12 @@ SIGNATURES = {
     "gof_slab_create": (_i, [C.POINTER(_vp), _i, _i, _i, C.POINTER(Grid), _vp, _i, _i, _i, _i]),
     "gof_slab_upload": (_i, [_vp, _i] + [_vp] * 11 + [_vp]),
     "gof_slab_pointers": (_i, [_vp, C.POINTER(_vp), _i]),
-    "gof_slab_phase_hash": (_i, [_vp, C.POINTER(_i), _vp]),
-    "gof_slab_phase_sort": (_i, [_vp, _i, _i, _f, C.POINTER(_i), _vp]),
     "gof_slab_phase_hash_async": (_i, [_vp, _vp]),
-    "gof_slab_phase_sort_async": (_i, [_vp, _i, _i, _f, _vp]),
+    "gof_slab_phase_sort_async": (_i, [_vp, _f, _vp]),
     "gof_slab_commit": (_i, [_vp, _i, _i, _i, _i]),
     "gof_slab_phase_force": (_i, [_vp, _i, _i, _i, _vp]),
+    "gof_slab_phase_force_interior": (_i, [_vp, _i, _vp]),
+    "gof_slab_phase_force_boundary": (_i, [_vp, _i, _i, _i, _vp]),
     "gof_slab_parity": (_i, [_vp]),
     "gof_slab_count": (_i, [_vp]),
     "gof_slab_download": (_i, [_vp] + [_vp] * 10 + [_vp]),

@@ -277,13 +277,15 @@ static int launch_force_t(const Geometry& g, const ForceArgs& a, cudaStream_t st
         GOF_CUDA(cudaFuncSetAttribute(k_force<BOIDS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    GOF_LAUNCH((k_force<BOIDS, MODE>), cdiv(a.home_count, kForceThreads), kForceThreads, smem, st, g, a);
+    GOF_LAUNCH((k_force<BOIDS, MODE>), cdiv(a.home_count + a.home_count2, kForceThreads), kForceThreads, smem, st,
+               g, a);
     return 0;
 }
 
+// a.home_count is the number of threads to launch (an upper bound when a.interior_words is set)
 static int launch_force(const Geometry& g, const ForceArgs& a, bool boids, int mode, cudaStream_t st)
 {
-    if (a.home_count <= 0) return 0;
+    if (a.home_count + a.home_count2 <= 0) return 0;
     if (mode == kModeIntegrate)
         return boids ? launch_force_t<true, kModeIntegrate>(g, a, st) : launch_force_t<false, kModeIntegrate>(g, a, st);
     return boids ? launch_force_t<true, kModeScatter>(g, a, st) : launch_force_t<false, kModeScatter>(g, a, st);
@@ -538,13 +540,13 @@ extern "C" int gof_setup_bins(const float* d_pos_x, const float* d_pos_y, const 
     if (n > 0) {
         MigrateOut none{};
         GOF_LAUNCH(k_hash_count<true>, cdiv(n, kBinThreads), kBinThreads, 0, st, (const float4*)nullptr,
-                   (const float4*)nullptr, (const float4*)nullptr, d_pos_x, d_pos_y, d_pos_z, n, g,
+                   (const float4*)nullptr, (const float4*)nullptr, d_pos_x, d_pos_y, d_pos_z, n, (const int*)nullptr, g,
                    d_particle_bins, d_bin_offsets, d_counts, none);
     }
     if (int rc = launch_scan<false>(d_counts, num_bins, tile_sums, d_starts, st)) return rc;
     if (n > 0) {
         GOF_LAUNCH(k_scatter_ids<true>, cdiv(n, kBinThreads), kBinThreads, 0, st, (const float4*)nullptr, n,
-                   d_particle_bins, d_bin_offsets, d_starts, slot_id);
+                   (const int*)nullptr, d_particle_bins, d_bin_offsets, d_starts, slot_id);
         GOF_LAUNCH(k_rank_indices, cdiv(n, kBinThreads), kBinThreads, 0, st, n, d_particle_bins, d_starts,
                    d_counts, slot_id, d_bin_offsets, d_particle_indices);
     }
@@ -714,6 +716,7 @@ struct gof_engine {
     int* counters = nullptr;                   // [0..2] leavers down / up / error, [4..7] sort results
     int n_slots = 0;        // resident slots before the sort (live + dead + arrivals)
     int n_halo[2] = {0, 0};
+    int lo_pop = 0, hi_pop = 0;  // populations of the two owned boundary layers (gof_slab_commit)
 
     // optional per-launch timing of the force kernel (bench.py roofline)
     bool timing = false;
@@ -764,8 +767,8 @@ static size_t engine_layout(gof_engine* e, char* base)
     e->stage_xyz = (float*)take(cap * 3 * sizeof(float));
     if (e->slab) {
         for (int d = 0; d < 2; ++d) {
-            e->mig_send[d] = (float4*)take((size_t)e->mig_capacity * 3 * sizeof(float4));
-            e->mig_recv[d] = (float4*)take((size_t)e->mig_capacity * 3 * sizeof(float4));
+            e->mig_send[d] = (float4*)take(((size_t)e->mig_capacity * 3 + 1) * sizeof(float4));
+            e->mig_recv[d] = (float4*)take(((size_t)e->mig_capacity * 3 + 1) * sizeof(float4));
         }
         e->counters = (int*)take(8 * sizeof(int));
     }
@@ -916,15 +919,16 @@ static int engine_bin(gof_engine* e, bool kick, cudaStream_t st)
     GOF_CUDA(cudaMemsetAsync(e->count, 0, (size_t)(g.num_cells + 2) * sizeof(int), st));
     MigrateOut none{};
     GOF_LAUNCH(k_hash_count<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->posw[0], e->veli[0], e->acc,
-               (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, n, g, e->cell_of, e->off,
-               e->count, none);
+               (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, n, (const int*)nullptr, g,
+               e->cell_of, e->off, e->count, none);
     if (int rc = launch_scan<false>(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
     if (packed)
         if (int rc = launch_scan<true>(e->count, g.num_cells + 1, e->tile_sums, e->pstart, st)) return rc;
     const int* layout = packed ? e->pstart : e->start;
-    GOF_LAUNCH(k_scatter_ids<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->veli[0], n, e->cell_of, e->off,
-               layout, e->slot_id);
-    GOF_LAUNCH(k_rank_gather_kick, cdiv(n, kBinThreads), kBinThreads, 0, st, n, e->cell_of, layout, e->count,
+    GOF_LAUNCH(k_scatter_ids<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->veli[0], n, (const int*)nullptr,
+               e->cell_of, e->off, layout, e->slot_id);
+    GOF_LAUNCH(k_rank_gather_kick, cdiv(n, kBinThreads), kBinThreads, 0, st, n, (const int*)nullptr, e->cell_of,
+               layout, e->count,
                e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1], e->cell_sorted,
                packed ? e->dup_a : (float4*)nullptr, packed ? e->dup_b : (float4*)nullptr, e->scalars,
                kick ? 1 : 0);
@@ -1206,19 +1210,19 @@ extern "C" int gof_slab_pointers(gof_engine* e, void** ptrs, int n_ptrs)
 
 namespace gof {
 // {live particles, population of the bottom owned layer, of the top owned layer, error flag}
-__global__ void k_slab_counts(const int* __restrict__ start, const int* __restrict__ counters_in,
+__global__ void k_slab_counts(const int* __restrict__ start, const int* __restrict__ error,
                               int* __restrict__ out, int num_cells, int per_layer, int top)
 {
     out[0] = start[num_cells];
     out[1] = start[2 * per_layer] - start[per_layer];
     out[2] = start[(top + 1) * per_layer] - start[top * per_layer];
-    out[3] = counters_in[2];
+    out[3] = *error;
 }
 }  // namespace gof
 
-/* Phase 1 (asynchronous): bin the resident particles; the ones that left the slab are packed
- * into the send buffers.  Afterwards counters[0..2] (pointer 10 of gof_slab_pointers) hold
- * {going down, going up, error flag} on the device; the host all-gathers them. */
+/* Phase 1: bin the resident particles; the ones that left the slab are packed into the two
+ * send buffers (header word = count).  Nothing comes back to the host: the buffers travel
+ * whole (fixed size) and phase 2 reads the counts on the device. */
 extern "C" int gof_slab_phase_hash_async(gof_engine* e, void* stream)
 {
     if (int rc = slab_ready(e, true)) return rc;
@@ -1226,76 +1230,52 @@ extern "C" int gof_slab_phase_hash_async(gof_engine* e, void* stream)
     const Geometry& g = e->geom;
     GOF_CUDA(cudaMemsetAsync(e->count, 0, (size_t)(g.num_cells + 2) * sizeof(int), st));
     GOF_CUDA(cudaMemsetAsync(e->counters, 0, 8 * sizeof(int), st));
+    GOF_CUDA(cudaMemsetAsync(e->mig_send[0], 0, sizeof(float4), st));
+    GOF_CUDA(cudaMemsetAsync(e->mig_send[1], 0, sizeof(float4), st));
     if (e->n > 0) {
-        MigrateOut mig{e->mig_send[0], e->mig_send[1], e->counters, e->mig_capacity};
+        MigrateOut mig{e->mig_send[0], e->mig_send[1], e->counters + 2, e->mig_capacity};
         GOF_LAUNCH(k_hash_count<false>, cdiv(e->n, kBinThreads), kBinThreads, 0, st, e->posw[0], e->veli[0], e->acc,
-                   (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, e->n, g, e->cell_of, e->off,
-                   e->count, mig);
+                   (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, e->n, (const int*)nullptr, g,
+                   e->cell_of, e->off, e->count, mig);
     }
     e->n_slots = e->n;
     return 0;
 }
 
-static int slab_check_hash(gof_engine* e, const int* h)
-{
-    if (h[2] == 1) return fail(GOF_E_STATE, "slab: a particle moved more than one layer in a step");
-    if (h[2] == 2 || h[0] > e->mig_capacity || h[1] > e->mig_capacity)
-        return fail(GOF_E_NOMEM, "slab: migration buffer overflow (raise migrate_capacity)");
-    return 0;
-}
-
-/* Phase 1, synchronous form: out_counts = {going down, going up}. */
-extern "C" int gof_slab_phase_hash(gof_engine* e, int* out_counts, void* stream)
-{
-    if (!out_counts) return fail(GOF_E_INVALID, "gof_slab_phase_hash: null output");
-    if (int rc = gof_slab_phase_hash_async(e, stream)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    int h[4] = {0, 0, 0, 0};
-    GOF_CUDA(cudaMemcpyAsync(h, e->counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    GOF_CUDA(cudaStreamSynchronize(st));
-    if (int rc = slab_check_hash(e, h)) return rc;
-    out_counts[0] = h[0];
-    out_counts[1] = h[1];
-    return 0;
-}
-
-/* Phase 2 (asynchronous): append the arrivals (already received into the recv buffers), bin
- * them, sort everything by cell and kick the velocities.  The maximum squared speed must have
- * been all-reduced over the slabs before this call when the timestep is adaptive.  Afterwards
- * counters[4..7] hold {live particles, population of the bottom owned layer, of the top one,
- * error flag}; the host all-gathers them and reports them back with gof_slab_commit. */
-extern "C" int gof_slab_phase_sort_async(gof_engine* e, int n_from_down, int n_from_up, float timestep,
-                                         void* stream)
+/* Phase 2: append the arrivals (the two received buffers), bin them, sort everything by cell
+ * and kick the velocities.  The maximum squared speed must have been all-reduced over the
+ * slabs before this call when the timestep is adaptive.  Afterwards counters[4..7] hold {live
+ * particles, population of the bottom owned layer, of the top one, error flag}; the host
+ * all-gathers them and reports them back with gof_slab_commit. */
+extern "C" int gof_slab_phase_sort_async(gof_engine* e, float timestep, void* stream)
 {
     if (int rc = slab_ready(e, true)) return rc;
-    if (n_from_down < 0 || n_from_up < 0) return fail(GOF_E_INVALID, "gof_slab_phase_sort: bad arguments");
-    if (n_from_down > e->mig_capacity || n_from_up > e->mig_capacity)
-        return fail(GOF_E_NOMEM, "slab: more arrivals than migrate_capacity");
     cudaStream_t st = (cudaStream_t)stream;
     const Geometry& g = e->geom;
-    const int arrivals = n_from_down + n_from_up;
-    const int total = e->n_slots + arrivals;
-    if (total > e->capacity) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
-    if (arrivals > 0) {
-        GOF_LAUNCH(k_append_arrivals, cdiv(arrivals, kBinThreads), kBinThreads, 0, st, e->mig_recv[0], n_from_down,
-                   e->mig_recv[1], n_from_up, e->n_slots, e->posw[0], e->veli[0], e->acc);
-        MigrateOut flag_only{nullptr, nullptr, e->counters, 0};
-        GOF_LAUNCH(k_hash_count<false>, cdiv(arrivals, kBinThreads), kBinThreads, 0, st, e->posw[0] + e->n_slots,
-                   e->veli[0] + e->n_slots, e->acc + e->n_slots, (const float*)nullptr, (const float*)nullptr,
-                   (const float*)nullptr, arrivals, g, e->cell_of + e->n_slots, e->off + e->n_slots, e->count,
-                   flag_only);
-    }
+    const int max_arrivals = 2 * e->mig_capacity;
+    int bound = e->n_slots + max_arrivals;  // slots that may be in use after the append
+    if (bound > e->capacity) bound = e->capacity;
+    if (e->n_slots + 64 > e->capacity) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
+    const int room = bound - e->n_slots;
+    int* words = e->counters;  // [0] arrivals, [1] slots in use ([2] is the error flag)
+    GOF_LAUNCH(k_append_arrivals, cdiv(max_arrivals, kBinThreads), kBinThreads, 0, st, e->mig_recv[0], e->mig_recv[1],
+               e->mig_capacity < room / 2 ? e->mig_capacity : room / 2, e->n_slots, e->posw[0], e->veli[0], e->acc,
+               words);
+    MigrateOut flag_only{nullptr, nullptr, e->counters + 2, 0};
+    GOF_LAUNCH(k_hash_count<false>, cdiv(room, kBinThreads), kBinThreads, 0, st, e->posw[0] + e->n_slots,
+               e->veli[0] + e->n_slots, e->acc + e->n_slots, (const float*)nullptr, (const float*)nullptr,
+               (const float*)nullptr, room, (const int*)words, g, e->cell_of + e->n_slots, e->off + e->n_slots,
+               e->count, flag_only);
     GOF_LAUNCH(k_prepare_dt, 1, 1, 0, st, e->scalars, e->parity, timestep < 0 ? -1.0f : timestep);
     if (int rc = launch_scan<false>(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
-    if (total > 0) {
-        GOF_LAUNCH(k_scatter_ids<false>, cdiv(total, kBinThreads), kBinThreads, 0, st, e->veli[0], total, e->cell_of,
-                   e->off, e->start, e->slot_id);
-        GOF_LAUNCH(k_rank_gather_kick, cdiv(total, kBinThreads), kBinThreads, 0, st, total, e->cell_of, e->start,
-                   e->count, e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1],
-                   e->cell_sorted, (float4*)nullptr, (float4*)nullptr, e->scalars, 1);
-    }
-    GOF_LAUNCH(k_slab_counts, 1, 1, 0, st, e->start, e->counters, e->counters + 4, g.num_cells, g.nbx * g.nby,
+    GOF_LAUNCH(k_scatter_ids<false>, cdiv(bound, kBinThreads), kBinThreads, 0, st, e->veli[0], bound,
+               (const int*)(words + 1), e->cell_of, e->off, e->start, e->slot_id);
+    GOF_LAUNCH(k_rank_gather_kick, cdiv(bound, kBinThreads), kBinThreads, 0, st, bound, (const int*)(words + 1),
+               e->cell_of, e->start, e->count, e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1],
+               e->veli[1], e->cell_sorted, (float4*)nullptr, (float4*)nullptr, e->scalars, 1);
+    GOF_LAUNCH(k_slab_counts, 1, 1, 0, st, e->start, e->counters + 2, e->counters + 4, g.num_cells, g.nbx * g.nby,
                g.nlz - 2);
+    e->n_slots = bound;  // upper bound until gof_slab_commit
     e->binned = true;
     e->binned_packed = false;
     return 0;
@@ -1305,51 +1285,19 @@ extern "C" int gof_slab_phase_sort_async(gof_engine* e, int n_from_down, int n_f
 extern "C" int gof_slab_commit(gof_engine* e, int n_live, int lo_pop, int hi_pop, int error)
 {
     if (int rc = slab_ready(e, true)) return rc;
-    if (error != 0) return fail(GOF_E_STATE, "slab: an arriving particle does not belong to this slab");
+    if (error == 1) return fail(GOF_E_STATE, "slab: a particle moved more than one layer in a step, or arrived in the wrong slab");
+    if (error == 2) return fail(GOF_E_NOMEM, "slab: migration buffer overflow (raise migrate_capacity)");
     if (n_live < 0 || n_live > e->capacity) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
     if (lo_pop > e->halo_capacity || hi_pop > e->halo_capacity)
         return fail(GOF_E_NOMEM, "slab: boundary layer larger than halo_capacity");
     e->n = n_live;
+    e->lo_pop = lo_pop;
+    e->hi_pop = hi_pop;
     return 0;
 }
 
-/* Phase 2, synchronous form: out_counts = {live, bottom layer population, top layer population}. */
-extern "C" int gof_slab_phase_sort(gof_engine* e, int n_from_down, int n_from_up, float timestep,
-                                   int* out_counts, void* stream)
+static int slab_timed_force(gof_engine* e, const ForceArgs& a, cudaStream_t st)
 {
-    if (!out_counts) return fail(GOF_E_INVALID, "gof_slab_phase_sort: null output");
-    if (int rc = gof_slab_phase_sort_async(e, n_from_down, n_from_up, timestep, stream)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    int h[4];
-    GOF_CUDA(cudaMemcpyAsync(h, e->counters + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    GOF_CUDA(cudaStreamSynchronize(st));
-    if (int rc = gof_slab_commit(e, h[0], h[1], h[2], h[3])) return rc;
-    out_counts[0] = h[0];
-    out_counts[1] = h[1];
-    out_counts[2] = h[2];
-    return 0;
-}
-
-/* Phase 3: the halo particles (n_lo from the slab below, then n_hi from the slab above)
- * have been received behind the owned ones and their per-cell counts into the count rows
- * of the two halo layers.  Forces + integration of the owned particles. */
-extern "C" int gof_slab_phase_force(gof_engine* e, int n_halo_lo, int n_halo_hi, int wrap_mode, void* stream)
-{
-    if (int rc = slab_ready(e, true)) return rc;
-    if (n_halo_lo < 0 || n_halo_hi < 0 || n_halo_lo > e->halo_capacity || n_halo_hi > e->halo_capacity)
-        return fail(GOF_E_NOMEM, "slab: halo larger than halo_capacity");
-    if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
-        return fail(GOF_E_INVALID, "gof_slab_phase_force: bad wrap_mode");
-    cudaStream_t st = (cudaStream_t)stream;
-    const Geometry& g = e->geom;
-    const int per_layer = g.nbx * g.nby;
-    GOF_LAUNCH(k_halo_starts, 2, kScanThreads, 0, st, e->count, e->start, per_layer, (g.nlz - 1) * per_layer, e->n,
-               e->n + n_halo_lo);
-    ForceArgs a;
-    engine_force_args(e, wrap_mode, &a);
-    a.pstart = e->start;
-    a.integrate = 1;
-    a.parity_out = e->parity ^ 1;
     const bool timed = e->timing && e->ev_used < kMaxTimedLaunches;
     if (timed) {
         while ((int)e->ev.size() < 2 * (e->ev_used + 1)) {
@@ -1359,13 +1307,83 @@ extern "C" int gof_slab_phase_force(gof_engine* e, int n_halo_lo, int n_halo_hi,
         }
         GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used], st));
     }
-    if (int rc = launch_force(g, a, e->species.has_boids, kModeIntegrate, st)) return rc;
+    if (int rc = launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st)) return rc;
     if (timed) {
         GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used + 1], st));
         ++e->ev_used;
     }
+    return 0;
+}
+
+/* Phase 3a: forces + integration of the owned particles that are in neither boundary layer.
+ * They need no halo, so this can be enqueued right after gof_slab_phase_sort_async while the
+ * host is still gathering sizes and moving the halo layers on another stream: the range is
+ * read from the device words of phase 2. */
+extern "C" int gof_slab_phase_force_interior(gof_engine* e, int wrap_mode, void* stream)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
+        return fail(GOF_E_INVALID, "gof_slab_phase_force_interior: bad wrap_mode");
+    if (e->layer_hi - e->layer_lo < 3) return 0;  // no interior layer
+    ForceArgs a;
+    engine_force_args(e, wrap_mode, &a);
+    a.pstart = e->start;
+    a.integrate = 1;
+    a.parity_out = e->parity ^ 1;
+    a.interior_words = e->counters + 4;
+    a.home_begin = 0;
+    a.home_count = e->n_slots;  // upper bound of the owned particles (set by phase 2)
+    return slab_timed_force(e, a, (cudaStream_t)stream);
+}
+
+/* Phase 3b: the halo particles (n_lo from the slab below, then n_hi from the slab above) have
+ * been received behind the owned ones and their per-cell counts into the count rows of the two
+ * halo layers: halo cell table, then the two boundary layers.  `skip_interior` = 0 also runs
+ * the interior here (the one-call form gof_slab_phase_force). */
+static int slab_force_boundary(gof_engine* e, int n_halo_lo, int n_halo_hi, int wrap_mode, bool with_interior,
+                               cudaStream_t st)
+{
+    if (n_halo_lo < 0 || n_halo_hi < 0 || n_halo_lo > e->halo_capacity || n_halo_hi > e->halo_capacity)
+        return fail(GOF_E_NOMEM, "slab: halo larger than halo_capacity");
+    if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
+        return fail(GOF_E_INVALID, "gof_slab_phase_force: bad wrap_mode");
+    const Geometry& g = e->geom;
+    const int per_layer = g.nbx * g.nby;
+    GOF_LAUNCH(k_halo_starts, 2, kScanThreads, 0, st, e->count, e->start, per_layer, (g.nlz - 1) * per_layer, e->n,
+               e->n + n_halo_lo);
+    ForceArgs a;
+    engine_force_args(e, wrap_mode, &a);
+    a.pstart = e->start;
+    a.integrate = 1;
+    a.parity_out = e->parity ^ 1;
+    const int owned = e->layer_hi - e->layer_lo;
+    if (with_interior || owned < 3) {
+        // everything in one launch (also the case when there is no interior layer)
+        if (int rc = slab_timed_force(e, a, st)) return rc;
+    } else {
+        // the bottom and the top owned layer in one launch
+        a.home_begin = 0;
+        a.home_count = e->lo_pop;
+        a.home_begin2 = e->n - e->hi_pop;
+        a.home_count2 = e->hi_pop;
+        if (int rc = slab_timed_force(e, a, st)) return rc;
+    }
     e->parity ^= 1;
     return 0;
+}
+
+extern "C" int gof_slab_phase_force_boundary(gof_engine* e, int n_halo_lo, int n_halo_hi, int wrap_mode,
+                                             void* stream)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    return slab_force_boundary(e, n_halo_lo, n_halo_hi, wrap_mode, false, (cudaStream_t)stream);
+}
+
+/* Phase 3 in one call (no overlap): halo table + all owned particles. */
+extern "C" int gof_slab_phase_force(gof_engine* e, int n_halo_lo, int n_halo_hi, int wrap_mode, void* stream)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    return slab_force_boundary(e, n_halo_lo, n_halo_hi, wrap_mode, true, (cudaStream_t)stream);
 }
 
 /* Current parity (which of the two max-speed slots describes the resident velocities). */

@@ -23,12 +23,14 @@ constexpr int kScanItems = 4;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 // Slab-mode send buffers for particles that left the owned layers (start-of-step
-// migration; see game_of_flies_b200/slab.py).  A record is three float4: {x, y, z, type},
-// {vx, vy, vz, id}, {ax, ay, az, 0}.  All pointers are null on a single GPU.
+// migration; see game_of_flies_b200/slab.py).  A buffer is one float4 header whose first
+// word is the record count, followed by records of three float4: {x, y, z, type},
+// {vx, vy, vz, id}, {ax, ay, az, 0}.  Buffers always travel whole (fixed size), so neither
+// side needs the count on the host.  All pointers are null on a single GPU.
 struct MigrateOut {
-    float4* down;    // records for the slab below
-    float4* up;      // records for the slab above
-    int* counters;   // [0] = number going down, [1] = going up, [2] = error flag
+    float4* down;    // header + records for the slab below
+    float4* up;      // header + records for the slab above
+    int* error;      // sticky error flag (1: moved more than a layer, 2: buffer overflow)
     int capacity;    // records per buffer
 };
 
@@ -44,10 +46,12 @@ __global__ void __launch_bounds__(kBinThreads)
 k_hash_count(const float4* __restrict__ posw, const float4* __restrict__ veli,
              const float4* __restrict__ acc, const float* __restrict__ px,
              const float* __restrict__ py, const float* __restrict__ pz, int n,
-             const __grid_constant__ Geometry g, int* __restrict__ cell_of,
-             int* __restrict__ off, int* __restrict__ count, MigrateOut mig)
+             const int* __restrict__ n_limit, const __grid_constant__ Geometry g,
+             int* __restrict__ cell_of, int* __restrict__ off, int* __restrict__ count,
+             MigrateOut mig)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_limit) n = min(n, *n_limit);  // slab mode: the real count lives on the device
     int cell = -1;
     if (i < n) {
         float x, y, z;
@@ -81,16 +85,17 @@ k_hash_count(const float4* __restrict__ posw, const float4* __restrict__ veli,
                     if (lz >= g.nlz || mig.down == nullptr) {
                         // more than one layer away, or an arrival that is not ours: cannot happen
                         // while a step moves a particle by far less than a bin (speed is capped)
-                        if (mig.counters) atomicExch(&mig.counters[2], 1);
+                        if (mig.error) atomicExch(mig.error, 1);
                     } else {
-                        const int k = atomicAdd(&mig.counters[down ? 0 : 1], 1);
+                        float4* buf = down ? mig.down : mig.up;
+                        const int k = atomicAdd(reinterpret_cast<int*>(buf), 1);
                         if (k < mig.capacity) {
-                            float4* rec = (down ? mig.down : mig.up) + 3 * (size_t)k;
+                            float4* rec = buf + 1 + 3 * (size_t)k;
                             rec[0] = posw[i];
                             rec[1] = veli[i];
                             rec[2] = acc[i];
                         } else {
-                            atomicExch(&mig.counters[2], 2);
+                            atomicExch(mig.error, 2);
                         }
                     }
                     cell = g.num_cells;
@@ -210,11 +215,12 @@ k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_pre
 // Arrival-order scatter of the ids into the cell segments (`start` may be the padded table).
 template <bool SOA>
 __global__ void __launch_bounds__(kBinThreads)
-k_scatter_ids(const float4* __restrict__ veli, int n, const int* __restrict__ cell_of,
-              const int* __restrict__ off, const int* __restrict__ start,
-              int* __restrict__ slot_id)
+k_scatter_ids(const float4* __restrict__ veli, int n, const int* __restrict__ n_limit,
+              const int* __restrict__ cell_of, const int* __restrict__ off,
+              const int* __restrict__ start, int* __restrict__ slot_id)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_limit) n = min(n, *n_limit);
     if (i >= n) return;
     slot_id[start[cell_of[i]] + off[i]] = SOA ? i : __float_as_int(veli[i].w);
 }
@@ -259,7 +265,8 @@ constexpr float kDummyPos = 1e18f;  // a padding slot sits here: (1e18)^2 * 3 st
 // is written a second time in the duplicated layout {x, x, y, y} {z, z, type, 0} that the
 // packed (two homes per lane) force kernel streams.
 __global__ void __launch_bounds__(kBinThreads)
-k_rank_gather_kick(int n, const int* __restrict__ cell_of, const int* __restrict__ pstart,
+k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict__ cell_of,
+                   const int* __restrict__ pstart,
                    const int* __restrict__ count, const int* __restrict__ slot_id,
                    int sentinel_cell, const float4* __restrict__ posw_in,
                    const float4* __restrict__ veli_in, const float4* __restrict__ acc_in,
@@ -269,6 +276,7 @@ k_rank_gather_kick(int n, const int* __restrict__ cell_of, const int* __restrict
                    int apply_kick)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_limit) n = min(n, *n_limit);
     if (i >= n) return;
     const int c = cell_of[i];
     if (c == sentinel_cell) return;  // dead slot: dropped by the sort
@@ -314,15 +322,22 @@ k_rank_gather_kick(int n, const int* __restrict__ cell_of, const int* __restrict
 namespace gof {
 
 // Slab mode: unpack the migration records received from the two neighbours behind the
-// resident particles (they are binned with the rest right after).
+// resident particles (they are binned with the rest right after).  The counts are the
+// header words of the received buffers; words[0] = arrivals, words[1] = slots in use.
 __global__ void __launch_bounds__(kBinThreads)
-k_append_arrivals(const float4* __restrict__ from_down, int n_down, const float4* __restrict__ from_up,
-                  int n_up, int base, float4* __restrict__ posw, float4* __restrict__ veli,
-                  float4* __restrict__ acc)
+k_append_arrivals(const float4* __restrict__ from_down, const float4* __restrict__ from_up, int capacity,
+                  int base, float4* __restrict__ posw, float4* __restrict__ veli,
+                  float4* __restrict__ acc, int* __restrict__ words)
 {
+    const int n_down = min(__float_as_int(from_down[0].x), capacity);
+    const int n_up = min(__float_as_int(from_up[0].x), capacity);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) {
+        words[0] = n_down + n_up;
+        words[1] = base + n_down + n_up;
+    }
     if (k >= n_down + n_up) return;
-    const float4* rec = k < n_down ? from_down + 3 * (size_t)k : from_up + 3 * (size_t)(k - n_down);
+    const float4* rec = k < n_down ? from_down + 1 + 3 * (size_t)k : from_up + 1 + 3 * (size_t)(k - n_down);
     posw[base + k] = rec[0];
     veli[base + k] = rec[1];
     acc[base + k] = rec[2];

@@ -38,6 +38,13 @@ struct ForceArgs {
     const float4* dup_a;      // packed kernel only: {x, x, y, y} per snapshot slot
     const float4* dup_b;      //                     {z, z, type bits, 0}
     int home_begin, home_count;
+    // Optional second range (slab mode: the two boundary layers in one launch): threads
+    // [0, home_count) cover home_begin.., threads [home_count, home_count + home_count2) cover
+    // home_begin2...
+    int home_begin2, home_count2;
+    // Slab mode, interior launch: the range is not known on the host yet; it is derived from
+    // the device words {live, bottom layer population, top layer population} (null otherwise).
+    const int* interior_words;
     const PairParam* table;   // [T*T]
     const unsigned* kind_rows;  // [T] bit j of row i set => (i, j) is of Boids kind
     const double* sep_exact;  // [T*T] args[0] / 5 in float64 (guard band of the separation radius)
@@ -442,9 +449,19 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     }
     __syncthreads();
 
+    int home_begin = a.home_begin, home_count = a.home_count;
+    if (a.interior_words) {  // owned particles that are in neither boundary layer
+        const int live = a.interior_words[0], lo = a.interior_words[1], hi = a.interior_words[2];
+        home_begin = lo;
+        home_count = live - lo - hi;
+        if (home_count <= 0) return;  // (block-uniform: one or two owned layers)
+    }
     const int local = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = local < a.home_count;
-    const int k = a.home_begin + (valid ? local : a.home_count - 1);
+    if (a.interior_words && local - (int)threadIdx.x >= home_count) return;  // whole block past the range
+    const bool valid = local < home_count + a.home_count2;
+    int k = home_begin + (local < home_count ? local : home_count - 1);
+    if (local >= home_count && a.home_count2 > 0)
+        k = a.home_begin2 + (valid ? local - home_count : a.home_count2 - 1);
 
     const float4 pi = a.posw[k];
     const float4 vi = a.veli[k];

@@ -5,7 +5,8 @@ layers.  Each slab is one `SlabEngine` (one GPU, normally one process): it owns 
 particles whose bin layer lies in [layer_lo, layer_hi) and, per step,
 
   1. bins its particles and hands the ones that left to the neighbouring slabs
-     (particle migration: records of position+type, velocity+id, acceleration);
+     (particle migration: fixed-size buffers of records position+type, velocity+id,
+     acceleration, the record count in a header word);
   2. sorts by cell, then exchanges its two boundary layers with the neighbours
      (halo-cell exchange: cell-ordered positions, velocities and per-cell counts,
      contiguous slices of the sorted arrays, so nothing is packed);
@@ -15,13 +16,14 @@ particles whose bin layer lies in [layer_lo, layer_hi) and, per step,
 `SlabRunner` sequences these phases and moves the buffers: with NCCL send/recv
 over NVLink when every process drives one slab (`DistComm`), or with plain device
 copies when several slabs live in one process (`LocalComm`, used to test the CUDA
-path on a single GPU).  The only collectives are tiny: an all-gather of the
-message sizes twice per step and, with the adaptive timestep, a MAX all-reduce of
-one word.  The physics is that of the single-GPU engine, bit for bit: the same
+path on a single GPU).  The only collectives are tiny: one all-gather of four
+words per slab and step (the halo message sizes) and, with the adaptive timestep,
+a MAX all-reduce of one word; the halo traffic runs under the interior forces.  The physics is that of the single-GPU engine, bit for bit: the same
 cells, the same order inside a cell (by particle id), the same summation order.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass
 
@@ -65,7 +67,11 @@ class SlabEngine:
         owned = self.layer_hi - self.layer_lo
         mean_layer = max(1, self.capacity // max(owned, 1))
         self.halo_capacity = int(halo_capacity or 4 * mean_layer + 1024)
-        self.migrate_capacity = int(migrate_capacity or max(4096, mean_layer))
+        # Migration buffers travel whole, so their size is part of the protocol: it must be the
+        # SAME on every slab (do not derive it from a per-slab quantity).  8192 records per
+        # direction and step is ~25% of a 32k-particle boundary layer; a step moves a particle
+        # by at most 0.4 (adaptive) so the expected flux is two orders of magnitude lower.
+        self.migrate_capacity = int(migrate_capacity or 8192)
         self.wrap_mode = int(wrap_mode)
         self._handle = C.c_void_p()
         _lib.check(self.lib.gof_slab_create(C.byref(self._handle), self.index, self.capacity, self.num_types,
@@ -140,38 +146,30 @@ class SlabEngine:
         return float(ms.value), int(k.value)
 
     # ---- phases ------------------------------------------------------------------------------
-    # Phases 1 and 2 only enqueue work.  Their results (message sizes) stay in four device
-    # words that the runner all-gathers straight from device memory: one host synchronisation
-    # per phase for all slabs together.
+    # Phases 1 and 2 only enqueue work.  Migration buffers travel whole (fixed size, the record
+    # count is their header word) so no size has to reach the host before the sort; the only
+    # words the host reads per step are phase 2's, all-gathered from device memory.
     def phase_hash(self):
         _lib.check(self.lib.gof_slab_phase_hash_async(self._handle, self._stream()))
 
-    def hash_words(self) -> torch.Tensor:
-        """int32[4] on the device after phase_hash: going down, going up, error flag, 0."""
-        return self._view(self._ptr[10], 4, torch.int32)
+    def _mig_words(self) -> int:
+        return 4 * (1 + 3 * self.migrate_capacity)
 
-    def check_hash(self, words):
-        if words[2] == 1:
-            raise _lib.GofError(_lib.E_STATE, "slab: a particle moved more than one layer in a step")
-        if words[2] == 2 or max(words[0], words[1]) > self.migrate_capacity:
-            raise _lib.GofError(_lib.E_NOMEM, "slab: migration buffer overflow (raise migrate_capacity)")
+    def mig_send(self, direction: int) -> torch.Tensor:
+        """The whole buffer (header + records) going to the slab below (0) / above (1)."""
+        return self._view(self._ptr[direction], self._mig_words(), torch.float32)
 
-    def mig_send(self, direction: int, n: int) -> torch.Tensor:
-        """direction 0: records going to the slab below, 1: above."""
-        return self._view(self._ptr[direction], n * self.REC, torch.float32)
-
-    def mig_recv(self, source: int, n: int) -> torch.Tensor:
-        """source 0: records coming from the slab below, 1: from above."""
-        return self._view(self._ptr[2 + source], n * self.REC, torch.float32)
+    def mig_recv(self, source: int) -> torch.Tensor:
+        """Where the buffer coming from the slab below (0) / above (1) is received."""
+        return self._view(self._ptr[2 + source], self._mig_words(), torch.float32)
 
     def speed_word(self) -> torch.Tensor:
         """max |v|^2 of the resident particles as its int32 bit pattern (orders like the float)."""
         return self._view(self._ptr[7 + int(self.lib.gof_slab_parity(self._handle))], 1, torch.int32)
 
-    def phase_sort(self, n_from_down: int, n_from_up: int, timestep=None):
+    def phase_sort(self, timestep=None):
         ts = -1.0 if timestep is None else float(timestep)
-        _lib.check(self.lib.gof_slab_phase_sort_async(self._handle, int(n_from_down), int(n_from_up), ts,
-                                                      self._stream()))
+        _lib.check(self.lib.gof_slab_phase_sort_async(self._handle, ts, self._stream()))
 
     def sort_words(self) -> torch.Tensor:
         """int32[4] on the device after phase_sort: live, bottom layer, top layer population, error flag."""
@@ -205,8 +203,23 @@ class SlabEngine:
         return self._layer_msgs(self.n_live + n_before, n, 0 if source == 0 else self.nlz - 1)
 
     def phase_force(self, n_halo_lo: int, n_halo_hi: int):
+        """Everything in one go (no overlap)."""
         _lib.check(self.lib.gof_slab_phase_force(self._handle, int(n_halo_lo), int(n_halo_hi), self.wrap_mode,
                                                  self._stream()))
+
+    def phase_force_interior(self):
+        """The owned layers that touch no halo; enqueued before the sizes are known on the host."""
+        _lib.check(self.lib.gof_slab_phase_force_interior(self._handle, self.wrap_mode, self._stream()))
+
+    def phase_force_boundary(self, n_halo_lo: int, n_halo_hi: int):
+        _lib.check(self.lib.gof_slab_phase_force_boundary(self._handle, int(n_halo_lo), int(n_halo_hi),
+                                                          self.wrap_mode, self._stream()))
+
+    def side_stream(self):
+        """A second stream for the halo traffic that runs under the interior forces."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.index)
+        return self._side
 
 
 @dataclass
@@ -314,7 +327,8 @@ class DistComm:
 class SlabRunner:
     """Drives the three phases of a step over this process's slabs."""
 
-    def __init__(self, slabs: dict, world_slabs: int, comm):
+    def __init__(self, slabs: dict, world_slabs: int, comm, overlap: bool = True):
+        self.overlap = overlap            # run the halo traffic under the interior forces
         self.slabs = dict(slabs)          # {global slab index: engine}
         self.world_slabs = int(world_slabs)
         self.comm = comm
@@ -329,51 +343,70 @@ class SlabRunner:
     def step(self, n_steps: int = 1, timestep=None):
         W = self.world_slabs
         for _ in range(n_steps):
-            # ---- 1. bin, pack leavers; exchange migration records --------------------------
+            # ---- 1. bin, pack leavers; the fixed-size migration buffers go to the neighbours ---
             for e in self.slabs.values():
                 e.phase_hash()
-            leave = self.comm.gather_words({s: e.hash_words() for s, e in self.slabs.items()})
-            for s, e in self.slabs.items():
-                e.check_hash(leave[s])
             transfers = []
-            for s in range(W):  # downward records first, then upward: one global order
-                n = leave[s][0]
+            for s in range(W):  # downward buffers first, then upward: one global order
                 transfers.append(Transfer(s, self._below(s),
-                                          send=lambda s=s, n=n: [self.slabs[s].mig_send(0, n)],
-                                          recv=lambda s=s, n=n: [self.slabs[self._below(s)].mig_recv(1, n)]))
+                                          send=lambda s=s: [self.slabs[s].mig_send(0)],
+                                          recv=lambda s=s: [self.slabs[self._below(s)].mig_recv(1)]))
             for s in range(W):
-                n = leave[s][1]
                 transfers.append(Transfer(s, self._above(s),
-                                          send=lambda s=s, n=n: [self.slabs[s].mig_send(1, n)],
-                                          recv=lambda s=s, n=n: [self.slabs[self._above(s)].mig_recv(0, n)]))
+                                          send=lambda s=s: [self.slabs[s].mig_send(1)],
+                                          recv=lambda s=s: [self.slabs[self._above(s)].mig_recv(0)]))
             self.comm.exchange(transfers)
             if timestep is None:
                 self.comm.allreduce_max([e.speed_word() for e in self.slabs.values()])
-            # ---- 2. append arrivals, sort; exchange boundary layers ---------------------------
-            for s, e in self.slabs.items():
-                e.phase_sort(leave[self._below(s)][1], leave[self._above(s)][0], timestep)
-            pops = self.comm.gather_words({s: e.sort_words() for s, e in self.slabs.items()})
-            for s, e in self.slabs.items():
-                e.commit(pops[s])
-            transfers = []
-            for s in range(W):  # every slab's bottom layer becomes the upper halo of the slab below
-                n = pops[s][1]
-                d = self._below(s)
-                # the receiver stores the upper halo behind its lower halo (= top layer of ITS lower slab)
-                n_before = pops[self._below(d)][2]
-                transfers.append(Transfer(s, d,
-                                          send=lambda s=s: self.slabs[s].halo_send(0),
-                                          recv=lambda d=d, n=n, nb=n_before: self.slabs[d].halo_recv(1, n, nb)))
-            for s in range(W):  # every slab's top layer becomes the lower halo of the slab above
-                n = pops[s][2]
-                d = self._above(s)
-                transfers.append(Transfer(s, d,
-                                          send=lambda s=s: self.slabs[s].halo_send(1),
-                                          recv=lambda d=d, n=n: self.slabs[d].halo_recv(0, n, 0)))
-            self.comm.exchange(transfers)
-            # ---- 3. forces + integration of the owned particles -----------------------------
-            for s, e in self.slabs.items():
-                e.phase_force(pops[self._below(s)][2], pops[self._above(s)][1])
+            # ---- 2. append arrivals (counts are read on the device), sort ---------------------
+            for e in self.slabs.values():
+                e.phase_sort(timestep)
+            # ---- 3a. interior forces start now; sizes + halo layers move underneath ------------
+            overlap = self.overlap and all(hasattr(e, "side_stream") for e in self.slabs.values())
+            if overlap:
+                main = {s: torch.cuda.current_stream(e.index) for s, e in self.slabs.items()}
+                sorted_ev = {s: main[s].record_event() for s in self.slabs}
+                for e in self.slabs.values():
+                    e.phase_force_interior()
+                first = next(iter(self.slabs.values()))
+                side = first.side_stream()
+                for s in self.slabs:
+                    side.wait_event(sorted_ev[s])
+                ctx = torch.cuda.stream(side)
+            else:
+                ctx = contextlib.nullcontext()
+            with ctx:
+                pops = self.comm.gather_words({s: e.sort_words() for s, e in self.slabs.items()})
+                for s, e in self.slabs.items():
+                    e.commit(pops[s])
+                transfers = []
+                for s in range(W):  # every slab's bottom layer becomes the upper halo of the slab below
+                    n = pops[s][1]
+                    d = self._below(s)
+                    # the receiver stores the upper halo behind its lower halo (= top layer of ITS lower slab)
+                    n_before = pops[self._below(d)][2]
+                    transfers.append(Transfer(s, d,
+                                              send=lambda s=s: self.slabs[s].halo_send(0),
+                                              recv=lambda d=d, n=n, nb=n_before: self.slabs[d].halo_recv(1, n, nb)))
+                for s in range(W):  # every slab's top layer becomes the lower halo of the slab above
+                    n = pops[s][2]
+                    d = self._above(s)
+                    transfers.append(Transfer(s, d,
+                                              send=lambda s=s: self.slabs[s].halo_send(1),
+                                              recv=lambda d=d, n=n: self.slabs[d].halo_recv(0, n, 0)))
+                self.comm.exchange(transfers)
+                # ---- 3b. the boundary layers once their halo is in: on the side stream too, so
+                # that their (few) blocks fill in next to the interior kernel instead of after it
+                for s, e in self.slabs.items():
+                    if overlap:
+                        e.phase_force_boundary(pops[self._below(s)][2], pops[self._above(s)][1])
+                    else:
+                        e.phase_force(pops[self._below(s)][2], pops[self._above(s)][1])
+                if overlap:
+                    done_ev = side.record_event()
+            if overlap:
+                for s in self.slabs:
+                    main[s].wait_event(done_ev)
             self.messages += 4 * W
 
     def gather_state(self, num_particles: int):

@@ -209,15 +209,21 @@ int gof_engine_last_timestep(gof_engine *e, float *out, void *stream);
  * send/recv (game_of_flies_b200/slab.py); every phase that produces sizes the host
  * needs synchronises `stream` and returns them.
  *
- *   1. gof_slab_phase_hash : bin resident particles, pack the ones that left the slab
- *                            -> exchange migration records with the two neighbours
- *   2. gof_slab_phase_sort : append arrivals, counting sort, step1 kick
- *                            -> exchange boundary layers (positions, velocities, counts)
- *   3. gof_slab_phase_force: halo cell table, neighbour forces + integrator (owned only)
+ *   1. gof_slab_phase_hash_async : bin resident particles, pack the ones that left the slab into the
+ *                                  two send buffers (header word = record count); the buffers travel
+ *                                  whole to the two neighbours, no size ever reaches the host
+ *   2. gof_slab_phase_sort_async : append arrivals (counts read from the received headers), counting
+ *                                  sort, step1 kick; leaves {live, bottom layer, top layer, error} in
+ *                                  device words, which the host all-gathers and hands back with
+ *                                  gof_slab_commit -> exchange boundary layers (positions, velocities
+ *                                  if needed, per-cell counts)
+ *   3. gof_slab_phase_force_interior (needs no halo, overlaps the exchange) +
+ *      gof_slab_phase_force_boundary, or gof_slab_phase_force for everything at once
  *
- * With an adaptive timestep the maximum squared speed (pointer 7 or 8 of
- * gof_slab_pointers, chosen by gof_slab_parity) is all-reduced (MAX, as int32 bit
- * patterns) between phases 1 and 2.  Results are bit-identical to the single-GPU engine.
+ * With an adaptive timestep the maximum squared speed (pointer 7 or 8 of gof_slab_pointers,
+ * chosen by gof_slab_parity) is all-reduced (MAX, as int32 bit patterns) between phases 1 and 2.
+ * One host synchronisation per step (the all-gather of phase 2's words).  Results are
+ * bit-identical to the single-GPU engine.
  * ---------------------------------------------------------------------- */
 int gof_slab_create(gof_engine **out, int device, int capacity, int num_types, const gof_grid *grid,
                     const double *parameter_matrix_host, int layer_lo, int layer_hi,
@@ -227,21 +233,21 @@ int gof_slab_upload(gof_engine *e, int num_particles, const float *pos_x_any, co
                     const float *pos_z_any, const float *vel_x_any, const float *vel_y_any,
                     const float *vel_z_any, const float *acc_x_any, const float *acc_y_any,
                     const float *acc_z_any, const int32_t *types_any, const int32_t *ids_any, void *stream);
-/* ptrs[0..10]: migration send down / send up / recv from below / recv from above (records of
- * three float4), snapshot positions, snapshot velocities (float4 each, cell order), cell counts
+/* ptrs[0..10]: migration send down / send up / recv from below / recv from above (one float4
+ * header + migrate_capacity records of three float4; always sent whole), snapshot positions, snapshot velocities (float4 each, cell order), cell counts
  * (int32), the two max-squared-speed slots (uint32 bit patterns), cell starts (int32), the 8 counter words (int32). */
 int gof_slab_pointers(gof_engine *e, void **ptrs, int n_ptrs);
-int gof_slab_phase_hash(gof_engine *e, int *out_counts2, void *stream);
-int gof_slab_phase_sort(gof_engine *e, int n_from_down, int n_from_up, float timestep,
-                        int *out_counts3, void *stream);
-/* Asynchronous forms: nothing is copied to the host.  The results stay in the device words
- * of pointer 10 ([0..2] = going down / going up / error after phase 1, [4..7] = live / bottom
- * layer / top layer / error after phase 2) so that the host can all-gather them straight from
- * device memory and synchronise once; it then reports phase 2's words with gof_slab_commit. */
 int gof_slab_phase_hash_async(gof_engine *e, void *stream);
-int gof_slab_phase_sort_async(gof_engine *e, int n_from_down, int n_from_up, float timestep, void *stream);
+int gof_slab_phase_sort_async(gof_engine *e, float timestep, void *stream);
+/* words of pointer 10: [2] sticky error flag, [4..7] = live / bottom layer / top layer / error
+ * after phase 2. */
 int gof_slab_commit(gof_engine *e, int n_live, int lo_pop, int hi_pop, int error);
 int gof_slab_phase_force(gof_engine *e, int n_halo_lo, int n_halo_hi, int wrap_mode, void *stream);
+/* Phase 3 split for overlap: the interior layers need no halo and can be enqueued right after
+ * gof_slab_phase_sort_async (their range is read from the device words), while sizes are gathered
+ * and halo layers move on another stream; the two boundary layers follow once the halo is in. */
+int gof_slab_phase_force_interior(gof_engine *e, int wrap_mode, void *stream);
+int gof_slab_phase_force_boundary(gof_engine *e, int n_halo_lo, int n_halo_hi, int wrap_mode, void *stream);
 int gof_slab_parity(const gof_engine *e);
 int gof_slab_count(const gof_engine *e);
 int gof_slab_download(gof_engine *e, float *pos_x_any, float *pos_y_any, float *pos_z_any,

@@ -13,6 +13,7 @@ import torch
 
 class FakeSlabEngine:
     REC = 12
+    CAP = 64  # records per migration buffer (fixed-size messages, count in the header)
 
     def __init__(self, parameter_matrix, limits, r_max, layer_lo, layer_hi, **_):
         self.pm = np.asarray(parameter_matrix, dtype=np.float64)
@@ -54,11 +55,14 @@ class FakeSlabEngine:
 
     def _records(self, mask):
         n = int(mask.sum())
-        rec = np.zeros((n, 12))
+        assert n <= self.CAP, "migration buffer overflow in the fake engine"
+        buf = np.zeros(4 + self.CAP * 12)
+        buf[0] = n
+        rec = buf[4:4 + n * 12].reshape(n, 12)
         rec[:, 0:3] = self.pos[:, mask].T; rec[:, 3] = self.types[mask]
         rec[:, 4:7] = self.vel[:, mask].T; rec[:, 7] = self.ids[mask]
         rec[:, 8:11] = self.acc[:, mask].T
-        return torch.from_numpy(rec.reshape(-1).copy())
+        return torch.from_numpy(buf)
 
     # ---- phases ----
     def phase_hash(self):
@@ -69,13 +73,6 @@ class FakeSlabEngine:
         keep = ~(down | up)
         self.pos, self.vel, self.acc = self.pos[:, keep], self.vel[:, keep], self.acc[:, keep]
         self.types, self.ids = self.types[keep], self.ids[keep]
-        self._words = torch.tensor([int(down.sum()), int(up.sum()), 0, 0], dtype=torch.int32)
-
-    def hash_words(self):
-        return self._words
-
-    def check_hash(self, words):
-        assert words[2] == 0
 
     def sort_words(self):
         return self._words
@@ -83,21 +80,22 @@ class FakeSlabEngine:
     def commit(self, words):
         assert words[3] == 0 and (self.n_live, self.lo_pop, self.hi_pop) == tuple(words[:3])
 
-    def mig_send(self, direction, n):
-        assert self._send[direction].numel() == n * 12
+    def mig_send(self, direction):
         return self._send[direction]
 
-    def mig_recv(self, source, n):
-        self._recv[source] = torch.zeros(n * 12, dtype=torch.float64)
+    def mig_recv(self, source):
+        self._recv[source] = torch.zeros(4 + self.CAP * 12, dtype=torch.float64)
         return self._recv[source]
 
     def speed_word(self):
         return self._speed
 
-    def phase_sort(self, n_from_down, n_from_up, timestep=None):
-        for src, n in ((0, n_from_down), (1, n_from_up)):
+    def phase_sort(self, timestep=None):
+        for src in (0, 1):
+            buf = self._recv[src].numpy()
+            n = int(buf[0])
             if n:
-                rec = self._recv[src].numpy().reshape(n, 12)
+                rec = buf[4:4 + n * 12].reshape(n, 12)
                 self.pos = np.concatenate([self.pos, rec[:, 0:3].T], axis=1)
                 self.vel = np.concatenate([self.vel, rec[:, 4:7].T], axis=1)
                 self.acc = np.concatenate([self.acc, rec[:, 8:11].T], axis=1)

@@ -23,7 +23,7 @@ def run_single(st, steps, timestep, wrap_mode):
     return out
 
 
-def run_slabs(st, world_slabs, steps, timestep, wrap_mode):
+def run_slabs(st, world_slabs, steps, timestep, wrap_mode, overlap=True):
     from game_of_flies_b200.slab import LocalComm, SlabEngine, SlabRunner, assign_to_slabs, split_layers
     grid = orc.grid_from_limits(st["limits"], st["r_max"])
     layers = split_layers(grid["num_bin_z"], world_slabs)
@@ -35,7 +35,7 @@ def run_slabs(st, world_slabs, steps, timestep, wrap_mode):
                        wrap_mode=wrap_mode)
         e.upload(st["pos"][:, m], st["types"][m], np.nonzero(m)[0], vel=st["vel"][:, m], acc=st["acc"][:, m])
         slabs[s] = e
-    runner = SlabRunner(slabs, world_slabs, LocalComm(world_slabs))
+    runner = SlabRunner(slabs, world_slabs, LocalComm(world_slabs), overlap=overlap)
     runner.step(steps, timestep)
     out = runner.gather_state(st["n"])
     moved = int((out["owner"] != owner).sum())
@@ -56,7 +56,8 @@ def test_slabs_reproduce_single_engine_bit_for_bit(kinds, counts, limits, speed,
     steps = 8
     for wrap_mode in (orc.WRAP_REFERENCE, orc.WRAP_MINIMAGE):
         want = run_single(st, steps, timestep, wrap_mode)
-        got, moved = run_slabs(st, world_slabs, steps, timestep, wrap_mode)
+        # with and without running the halo traffic under the interior forces
+        got, moved = run_slabs(st, world_slabs, steps, timestep, wrap_mode, overlap=(wrap_mode == orc.WRAP_REFERENCE))
         assert (got["owner"] >= 0).all(), "every particle must be owned by exactly one slab"
         assert moved > 0, "the run should exercise migration between slabs"
         for k in ("pos", "vel", "acc"):
