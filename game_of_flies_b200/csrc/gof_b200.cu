@@ -309,7 +309,7 @@ static int launch_scan(const int* in, int m, int* tile_sums, int* out, cudaStrea
 
 static size_t force2_smem_bytes(int T)
 {
-    return (size_t)T * T * (sizeof(PairParam) + sizeof(float4) + sizeof(float)) + 16;
+    return (size_t)T * T * sizeof(PairParam) + (size_t)T * T * T * (2 * sizeof(float4) + sizeof(float2)) + 16;
 }
 
 // the packed two-homes-per-lane Clusters kernel; `slots` = upper bound of padded slots
@@ -905,7 +905,10 @@ extern "C" int gof_engine_upload(gof_engine* e, const float* px, const float* py
 
 // Which force kernel a step uses: the packed two-homes kernel needs every species pair to be
 // of the Clusters kind (its profile is evaluated branch-free for both homes at once).
-static bool engine_packed(const gof_engine* e) { return e->want_packed && !e->species.has_boids; }
+static bool engine_packed(const gof_engine* e)
+{
+    return e->want_packed && !e->species.has_boids && e->T <= kPackedMaxTypes;
+}
 
 // setup_bins on the resident state: posw[0]/veli[0]/acc (rest order) -> posw[1]/veli[1]
 // (cell order, velocities kicked by step1 when `kick`), cell tables filled.  For the packed

@@ -34,30 +34,33 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __
 // Packed species parameters of (home type 0, home type 1) x current neighbour type for
 //   f(d) = s1 * (hw - |d - mid|) + cc * min(d - r_min, 0),   cc = -k0 - s1
 // which equals the reference profile: the triangle for d >= r_min, f_min - k0 d below.
+// They come out of shared memory already paired: the block builds a T^3 table indexed
+// (t0, t1, tj) whose entries are {-r_min0, -r_min1, -mid0, -mid1}, {-s1_0, -s1_1, f_max0,
+// f_max1}, {cc0, cc1}, so that one 16-byte load lands two operands of a packed instruction
+// in an aligned register pair and nothing has to be shuffled.
 struct PackedParams {
-    float2 nrmin;  // -r_min
-    float2 nmid;   // -mid
-    float2 ns1;    // -s1
-    float2 fmax;   // s1 * hw
-    float2 cc;     // -k0 - s1
-    int type;      // neighbour type these belong to
+    float4 q0;  // -r_min (x, y), -mid (z, w)
+    float4 q1;  // -s1 (x, y), f_max (z, w)
+    float2 q2;  // cc
+    int type;   // neighbour type these belong to
 };
 
-// derived per-pair table in shared memory: {-r_min, -mid, -s1, f_max} and cc
+constexpr int kPackedMaxTypes = 9;  // T^3 * 40 B of shared memory: 29 KB at T = 9 (the reference UI's maximum)
+
 struct Derived {
-    const float4* d4;
-    const float* cc;
+    const float4* q0;
+    const float4* q1;
+    const float2* q2;
     int T;
+    int row;  // (t0 * T + t1) * T of this lane
 };
 
-__device__ __forceinline__ void load_params(PackedParams& p, const Derived& d, int t0, int t1, int tj)
+__device__ __forceinline__ void load_params(PackedParams& p, const Derived& d, int tj)
 {
-    const float4 a = d.d4[t0 * d.T + tj], b = d.d4[t1 * d.T + tj];
-    p.nrmin = f2(a.x, b.x);
-    p.nmid = f2(a.y, b.y);
-    p.ns1 = f2(a.z, b.z);
-    p.fmax = f2(a.w, b.w);
-    p.cc = f2(d.cc[t0 * d.T + tj], d.cc[t1 * d.T + tj]);
+    const int k = d.row + tj;
+    p.q0 = d.q0[k];
+    p.q1 = d.q1[k];
+    p.q2 = d.q2[k];
     p.type = tj;
 }
 
@@ -116,24 +119,27 @@ __device__ __noinline__ float3 repair_pair2(const Geometry& g, float xi, float y
 }
 
 // One neighbour against the lane's two home particles.  Returns the two squared
-// distances (for the repair vote of the caller).
+// distances; `band` / `dmin` collect what the caller's repair vote needs.
 template <bool LOWFIX>
 __device__ __forceinline__ float2 neighbour2(Home2& h, PackedParams& pp, const Derived& der,
-                                             const Geometry& g, const Image2& im,
-                                             const float4 A, const float4 B)
+                                             const Geometry& g, const Image2& im, float2 nmid2,
+                                             float hw2, const float4 A, const float4 B,
+                                             bool& band, float& dmin)
 {
     // neighbour - home (the force below is accumulated with the matching sign)
     float2 dx = add2(f2(A.x, A.y), im.nx), dy = add2(f2(A.z, A.w), im.ny), dz = add2(f2(B.x, B.y), im.nz);
     if (LOWFIX) { dx = add2(dx, im.nlx); dy = add2(dy, im.nly); dz = add2(dz, im.nlz); }
     const float2 d2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, f2(kTinyD2, kTinyD2))));
     const int tj = __float_as_int(B.z);
-    if (tj != pp.type) load_params(pp, der, h.t0, h.t1, tj);
+    // neighbours are ordered by id inside a cell and ids are numbered species by species: the
+    // type changes about once per six neighbours.  The vote makes this a real (mostly
+    // not-taken) branch instead of a handful of predicated loads on every neighbour.
+    if (__any_sync(__activemask(), tj != pp.type)) load_params(pp, der, tj);
     const float2 inv = f2(fast_rsqrt(d2.x), fast_rsqrt(d2.y));
-    const float2 dist = mul2(d2, inv);
-    const float2 u = add2(dist, pp.nrmin);
-    const float2 t = add2(dist, pp.nmid);
-    float2 f = fma2(pp.ns1, f2(fabsf(t.x), fabsf(t.y)), pp.fmax);
-    f = fma2(pp.cc, f2(fminf(u.x, 0.0f), fminf(u.y, 0.0f)), f);
+    const float2 u = fma2(d2, inv, f2(pp.q0.x, pp.q0.y));  // d - r_min
+    const float2 t = fma2(d2, inv, f2(pp.q0.z, pp.q0.w));  // d - mid
+    float2 f = fma2(f2(pp.q1.x, pp.q1.y), f2(fabsf(t.x), fabsf(t.y)), f2(pp.q1.z, pp.q1.w));
+    f = fma2(pp.q2, f2(fminf(u.x, 0.0f), fminf(u.y, 0.0f)), f);
     const float2 mask = f2(d2.x < g.r2_lo ? 1.0f : 0.0f, d2.y < g.r2_lo ? 1.0f : 0.0f);
     const float2 s = mul2(mul2(f, inv), mask);
     // force on home = -f * (home - neighbour) / dist = +s * (neighbour - home); the self
@@ -141,6 +147,10 @@ __device__ __forceinline__ float2 neighbour2(Home2& h, PackedParams& pp, const D
     h.ax = fma2(s, dx, h.ax);
     h.ay = fma2(s, dy, h.ay);
     h.az = fma2(s, dz, h.az);
+    // repair vote: inside the guard band (|d2 - centre| < half width) or at/below 1e-10
+    const float2 c = add2(d2, nmid2);
+    band |= (fabsf(c.x) < hw2) | (fabsf(c.y) < hw2);
+    dmin = fminf(dmin, fminf(d2.x, d2.y));
     return d2;
 }
 
@@ -178,22 +188,27 @@ __device__ __forceinline__ void run_pairs2(Home2& h, PackedParams& pp, const Der
     h.ax = h.ay = h.az = f2(0.f, 0.f);
     const float4* __restrict__ da = a.dup_a;
     const float4* __restrict__ db = a.dup_b;
+    // centre and half width of the guard band [r2_lo, r2_hi) (a little wider: a false alarm only
+    // costs a trip through the repair code, which decides exactly)
+    const float mid = 0.5f * (g.r2_lo + g.r2_hi), hw2 = 0.51f * (g.r2_hi - g.r2_lo) + 1e-30f;
+    const float2 nmid2 = f2(-mid, -mid);
     int j = s;
     for (; j + 2 <= e; j += 2) {
         const float4 A0 = ldg4(da + j), B0 = ldg4(db + j), A1 = ldg4(da + j + 1), B1 = ldg4(db + j + 1);
-        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, A0, B0);
-        const float2 d1 = neighbour2<LOWFIX>(h, pp, der, g, im, A1, B1);
-        const float lo4 = fminf(fminf(d0.x, d0.y), fminf(d1.x, d1.y));
-        const bool band = (!(d0.x < g.r2_lo) && d0.x < g.r2_hi) | (!(d0.y < g.r2_lo) && d0.y < g.r2_hi) |
-                          (!(d1.x < g.r2_lo) && d1.x < g.r2_hi) | (!(d1.y < g.r2_lo) && d1.y < g.r2_hi);
-        if (band | (lo4 <= 1e-10f)) {
+        bool band = false;
+        float dmin = 1.0f;
+        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, A0, B0, band, dmin);
+        const float2 d1 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, A1, B1, band, dmin);
+        if (band | (dmin <= 1e-10f)) {
             if (needs_repair2(g, d0)) repair2(h, tab, der.T, g, im, A0, B0, d0);
             if (needs_repair2(g, d1)) repair2(h, tab, der.T, g, im, A1, B1, d1);
         }
     }
     if (j < e) {
         const float4 A0 = ldg4(da + j), B0 = ldg4(db + j);
-        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, A0, B0);
+        bool band = false;
+        float dmin = 1.0f;
+        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, A0, B0, band, dmin);
         if (needs_repair2(g, d0)) repair2(h, tab, der.T, g, im, A0, B0, d0);
     }
     h.ax = add2(h.ax, ax0); h.ay = add2(h.ay, ay0); h.az = add2(h.az, az0);
@@ -220,19 +235,23 @@ k_force2(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a
     extern __shared__ float4 smem_raw[];
     const int T = a.T;
     PairParam* tab = reinterpret_cast<PairParam*>(smem_raw);  // AoS table: cold paths
-    float4* d4 = reinterpret_cast<float4*>(tab + T * T);
-    float* ccs = reinterpret_cast<float*>(d4 + T * T);
-    for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
-        const PairParam pp = a.table[q];
-        tab[q] = pp;
+    float4* q0 = reinterpret_cast<float4*>(tab + T * T);
+    float4* q1 = q0 + T * T * T;
+    float2* q2 = reinterpret_cast<float2*>(q1 + T * T * T);
+    for (int q = threadIdx.x; q < T * T; q += blockDim.x) tab[q] = a.table[q];
+    for (int q = threadIdx.x; q < T * T * T; q += blockDim.x) {
+        const int tj = q % T, t1 = (q / T) % T, t0 = q / (T * T);
         // clusters: a = {r_min, k0, f_min, mid}, b = {s1, f_max}
-        d4[q] = make_float4(-pp.a.x, -pp.a.w, -pp.b.x, pp.b.y);
-        ccs[q] = -pp.a.y - pp.b.x;
+        const PairParam p0 = a.table[t0 * T + tj], p1 = a.table[t1 * T + tj];
+        q0[q] = make_float4(-p0.a.x, -p1.a.x, -p0.a.w, -p1.a.w);
+        q1[q] = make_float4(-p0.b.x, -p1.b.x, p0.b.y, p1.b.y);
+        q2[q] = make_float2(-p0.a.y - p0.b.x, -p1.a.y - p1.b.x);
     }
     __syncthreads();
     Derived der;
-    der.d4 = d4;
-    der.cc = ccs;
+    der.q0 = q0;
+    der.q1 = q1;
+    der.q2 = q2;
     der.T = T;
 
     // padded slot index space: this lane owns slots k0 and k0 + 1 of one cell
@@ -252,9 +271,11 @@ k_force2(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a
     h.ax = h.ay = h.az = f2(0.f, 0.f);
     h.t0 = __float_as_int(p0.w);
     h.t1 = __float_as_int(p1.w);  // padding slots carry type 0
+    der.row = (h.t0 * T + h.t1) * T;
     PackedParams pp;
     pp.type = -1;
-    pp.nrmin = pp.nmid = pp.ns1 = pp.fmax = pp.cc = f2(0.f, 0.f);
+    pp.q0 = pp.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    pp.q2 = f2(0.f, 0.f);
 
     const int cx = c % g.nbx;
     const int cyz = c / g.nbx;
