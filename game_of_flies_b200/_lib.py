@@ -70,6 +70,8 @@ SIGNATURES = {
     "gof_engine_accelerate": (_i, [_vp, _i, _vp]),
     "gof_engine_download": (_i, [_vp] + [_vp] * 9 + [_vp]),
     "gof_engine_snapshot": (_i, [_vp, _vp, _vp]),
+    "gof_engine_snapshot_stage": (_i, [_vp, _vp]),
+    "gof_engine_snapshot_copy": (_i, [_vp, _vp, _vp]),
     "gof_engine_read_bins": (_i, [_vp] + [_vp] * 4 + [_vp]),
     "gof_engine_set_kernel": (_i, [_vp, _i]),
     "gof_engine_timing": (_i, [_vp, _i]),

@@ -1047,6 +1047,29 @@ extern "C" int gof_engine_snapshot(gof_engine* e, float* xyz, void* stream)
     return 0;
 }
 
+/* The two halves of gof_engine_snapshot, for double buffering: `stage` runs the un-permute
+ * kernel into the engine's device staging buffer on `stream` (it must precede the next step,
+ * which rewrites the state); `copy` moves the staged frame to xyz_any on `stream`, typically a
+ * side stream that waited for the stage, so that the next step overlaps the transfer.  The
+ * next `stage` must wait for the previous `copy`. */
+extern "C" int gof_engine_snapshot_stage(gof_engine* e, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    const int n = e->n;
+    GOF_LAUNCH(k_snapshot, cdiv(n, kEwThreads), kEwThreads, 0, (cudaStream_t)stream, e->posw[0], e->veli[0], n,
+               e->stage_xyz);
+    return 0;
+}
+
+extern "C" int gof_engine_snapshot_copy(gof_engine* e, float* xyz, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    if (!xyz) return fail(GOF_E_INVALID, "gof_engine_snapshot_copy: null output");
+    GOF_CUDA(cudaMemcpyAsync(xyz, e->stage_xyz, (size_t)e->n * 3 * sizeof(float), cudaMemcpyDefault,
+                             (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" int gof_engine_read_bins(gof_engine* e, int32_t* particle_bins, int32_t* bin_counts,
                                     int32_t* bin_starts, int32_t* particle_indices, void* stream)
 {

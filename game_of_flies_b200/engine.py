@@ -130,6 +130,14 @@ class ParticleEngine:
         """Positions as [N][3] fp32 into a pinned tensor / numpy array / CUDA tensor (async)."""
         _lib.check(self.lib.gof_engine_snapshot(self._handle, _any_ptr(xyz), self._stream()))
 
+    def snapshot_stage(self):
+        """Un-permute the positions into the device staging buffer (current stream)."""
+        _lib.check(self.lib.gof_engine_snapshot_stage(self._handle, self._stream()))
+
+    def snapshot_copy(self, xyz):
+        """Copy the staged frame out (current stream: make it a side stream)."""
+        _lib.check(self.lib.gof_engine_snapshot_copy(self._handle, _any_ptr(xyz), self._stream()))
+
     def read_bins(self):
         """particle_bins, bin_counts, bin_starts, particle_indices of the last step (reference layout)."""
         cells = int(self.grid.num_cells)

@@ -143,10 +143,14 @@ class Simulation:
         self.engine.upload((self.pos_x, self.pos_y, self.pos_z), self.particle_type_index_array,
                            vel=(self.vel_x, self.vel_y, self.vel_z),
                            acc=(self.acc_x, self.acc_y, self.acc_z))
-        # snapshots stream to pinned host memory on a side stream (viewer / recorder)
-        self._xyz_pinned = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+        # snapshots stream to pinned host memory on a side stream (viewer / recorder): two pinned
+        # frames, so that frame k is copied out (and written to disk) while step k+1 computes
+        self._xyz_pinned = [torch.empty((n, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)]
         self._snap_stream = torch.cuda.Stream(device=self.engine.index)
-        self._snap_event = torch.cuda.Event()
+        self._staged = torch.cuda.Event()      # un-permute kernel of the latest frame done
+        self._copied = [torch.cuda.Event(), torch.cuda.Event()]  # frame landed in pinned[b]
+        self._frame_buf = 0
+        self._copy_pending = False
         self._torch = torch
 
     # ------------------------------------------------------------------------------------
@@ -158,25 +162,37 @@ class Simulation:
         self.parameter_matrix[:5, i, j] = params
         self.engine.set_parameters(self.parameter_matrix)
 
-    def _snapshot_async(self):
+    def _snapshot_begin(self) -> int:
+        """Enqueue the snapshot of the current state; returns the pinned buffer it will land in.
+        Compute stream: un-permute kernel into the device staging frame (must run before the next
+        step rewrites the state).  Side stream: the device-to-host copy, overlapping that step."""
         torch = self._torch
         main = torch.cuda.current_stream(self.engine.index)
-        self._snap_stream.wait_stream(main)
+        b = self._frame_buf
+        self._frame_buf ^= 1
+        if self._copy_pending:
+            main.wait_event(self._copied[b ^ 1])  # the staging frame is free once the last copy left it
+        self.engine.snapshot_stage()
+        self._staged.record(main)
         with torch.cuda.stream(self._snap_stream):
-            self.engine.snapshot_into(self._xyz_pinned)
-            self._snap_event.record(self._snap_stream)
-        # the next step rewrites the state the snapshot kernel reads
-        main.wait_stream(self._snap_stream)
+            self._snap_stream.wait_event(self._staged)
+            self.engine.snapshot_copy(self._xyz_pinned[b])
+            self._copied[b].record(self._snap_stream)
+        self._copy_pending = True
+        return b
 
-    def update(self):
-        self.core_step()
-        self._snapshot_async()
-        self._snap_event.synchronize()
-        xyz = self._xyz_pinned.numpy()
+    def _snapshot_end(self, b: int):
+        """Wait for frame `b` and publish it as `output` (float64 [N][3], particle order)."""
+        self._copied[b].synchronize()
+        xyz = self._xyz_pinned[b].numpy()
         self.output[:, :] = xyz
         self.pos_x[:] = xyz[:, 0]
         self.pos_y[:] = xyz[:, 1]
         self.pos_z[:] = xyz[:, 2]
+
+    def update(self):
+        self.core_step()
+        self._snapshot_end(self._snapshot_begin())
 
     def synchronize(self):
         self._torch.cuda.synchronize(self.engine.index)
@@ -206,13 +222,24 @@ class Simulation:
             from tqdm import tqdm
             steps = tqdm(steps)
         start = time.perf_counter()
+        pending = None
         for _ in steps:
             if record is not None:
-                self.update()
-                self.record()
-                self.frame += 1
+                # pipelined update() + record(): frame k-1 is published and written while the
+                # GPU computes step k (same files, same order as the reference's loop)
+                self.core_step()
+                b = self._snapshot_begin()
+                if pending is not None:
+                    self._snapshot_end(pending)
+                    self.record()
+                    self.frame += 1
+                pending = b
             else:
                 self.core_step()
+        if pending is not None:
+            self._snapshot_end(pending)
+            self.record()
+            self.frame += 1
         self.synchronize()
         return time.perf_counter() - start
 

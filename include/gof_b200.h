@@ -177,6 +177,13 @@ int gof_engine_download(gof_engine *e, float *pos_x_any, float *pos_y_any, float
  * asynchronous on `stream`. */
 int gof_engine_snapshot(gof_engine *e, float *xyz_any, void *stream);
 
+/* gof_engine_snapshot in two halves for double buffering: `stage` un-permutes into the engine's
+ * device staging buffer (enqueue it on the compute stream, before the next step), `copy` moves
+ * the staged frame out (enqueue it on a side stream that waited for the stage).  The next stage
+ * must wait for the previous copy. */
+int gof_engine_snapshot_stage(gof_engine *e, void *stream);
+int gof_engine_snapshot_copy(gof_engine *e, float *xyz_any, void *stream);
+
 /* The binning of the LAST step/upload in the reference's layout, particle order:
  * particle_bins[N], bin_counts[num_cells], bin_starts[num_cells], particle_indices[N].
  * Any pointer may be NULL. */

@@ -291,6 +291,32 @@ def test_simulation_class_drop_in(gof, tmp_path):
     assert f.shape == (800, 3)
 
 
+def test_recorder_pipeline_writes_the_same_frames_as_stepwise_updates(gof, tmp_path):
+    """blind_run(record=...) streams frame k to pinned memory (and to disk) while step k+1
+    computes; the files must equal what update() + output gives step by step, and be readable
+    the way the reference's npy2vid.py reads them (state.npz keys, frames/*.npy)."""
+    from game_of_flies_b200.simulation import Simulation
+    args = (np.array([500, 400, 300]), np.array([0]))
+    kw = dict(seed=954, limits=(90, 90, 90))
+    rec = str(tmp_path / "rec")
+    a = Simulation(*args, **kw)
+    a.update()
+    a.blind_run(7, rec)
+    b = Simulation(*args, **kw)
+    b.update()
+    frames = []
+    for _ in range(7):
+        b.update()
+        frames.append(b.output.copy())
+    names = sorted(os.listdir(os.path.join(rec, "frames")))
+    assert names == [f"{k:05}.npy" for k in range(7)]
+    for k, nm in enumerate(names):
+        assert np.array_equal(np.load(os.path.join(rec, "frames", nm)), frames[k]), nm
+    state = np.load(os.path.join(rec, "state.npz"))
+    assert set(state.files) >= {"type_array", "limits", "parameter_matrix", "num_particles", "seed"}
+    assert np.array_equal(state["type_array"][: int(state["num_particles"])], a.particle_type_index_array)
+
+
 def test_full_size_properties_clusters3d_1m(gof):
     """BASELINE.json configs[1] (Clusters 3D, 5 species, N=1M): size-independent properties."""
     n_per = 200_000
@@ -334,3 +360,23 @@ def test_full_size_properties_clusters3d_1m(gof):
             continue  # the reference's z-wrap quirk applies there; covered by the oracle tests
         assert np.linalg.norm(acc[:, i] - want) <= 1e-5 * max(np.linalg.norm(want), 10.0)
     e.close(); e2.close()
+
+
+def test_full_size_properties_boids3d_4m(gof):
+    """BASELINE.json configs[2] (Boids 3D, N=4M): size-independent properties + sampled brute force
+    of the per-type neighbour counts (exact integers) that drive cohesion / alignment."""
+    n_per = 4_000_000 // 3
+    st = random_state([n_per] * 3, (660.0, 660.0, 660.0), seed=2, kinds="boids", speed=8.0)
+    e = engine_from_state(gof, st)
+    e.step(2)
+    pb, cnt, stt, idx = e.read_bins()
+    n = st["n"]
+    assert cnt.sum() == n and np.array_equal(np.sort(idx), np.arange(n))
+    assert np.all(np.diff(pb[idx]) >= 0)
+    same = np.diff(pb[idx]) == 0
+    assert np.all(np.diff(idx)[same] > 0)
+    out = e.download(pos=True, vel=True, acc=True)
+    for k in ("pos", "vel", "acc"):
+        assert np.all(np.isfinite(out[k]))
+    assert np.all(out["pos"] >= 0) and np.all(out["pos"] <= st["limits"][:, None])
+    e.close()
