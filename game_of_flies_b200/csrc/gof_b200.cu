@@ -696,7 +696,6 @@ struct gof_engine {
     float4 *posw[2] = {nullptr, nullptr}, *veli[2] = {nullptr, nullptr}, *acc = nullptr;
     int *cell_of = nullptr, *off = nullptr, *slot_id = nullptr, *slot_src = nullptr, *cell_sorted = nullptr;
     int *count = nullptr, *start = nullptr, *pstart = nullptr, *tile_sums = nullptr;
-    float4 *dup_a = nullptr, *dup_b = nullptr;  // duplicated snapshot of the packed kernel
     int slot_capacity = 0;                      // capacity + num_cells + 2 (even-padded segments)
     StepScalars* scalars = nullptr;
     DeviceSpecies dspecies{};
@@ -745,8 +744,6 @@ static size_t engine_layout(gof_engine* e, char* base)
     e->veli[0] = (float4*)take(cap * sizeof(float4));
     e->posw[1] = (float4*)take(slots * sizeof(float4));
     e->veli[1] = (float4*)take(slots * sizeof(float4));
-    e->dup_a = (float4*)take(slots * sizeof(float4));
-    e->dup_b = (float4*)take(slots * sizeof(float4));
     e->acc = (float4*)take(cap * sizeof(float4));
     e->cell_of = (int*)take(cap * sizeof(int));
     e->off = (int*)take(cap * sizeof(int));
@@ -933,8 +930,7 @@ static int engine_bin(gof_engine* e, bool kick, cudaStream_t st)
     GOF_LAUNCH(k_rank_gather_kick, cdiv(n, kBinThreads), kBinThreads, 0, st, n, (const int*)nullptr, e->cell_of,
                layout, e->count,
                e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1], e->cell_sorted,
-               packed ? e->dup_a : (float4*)nullptr, packed ? e->dup_b : (float4*)nullptr, e->scalars,
-               kick ? 1 : 0);
+               packed ? 1 : 0, e->scalars, kick ? 1 : 0);
     e->binned = true;
     e->binned_packed = packed;
     return 0;
@@ -955,8 +951,6 @@ static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
     a->cell_sorted = e->cell_sorted;
     a->start = e->start;
     a->pstart = engine_packed(e) ? e->pstart : e->start;
-    a->dup_a = e->dup_a;
-    a->dup_b = e->dup_b;
     a->count = e->count;
     a->home_begin = 0;
     a->home_count = e->n;
@@ -1298,7 +1292,7 @@ extern "C" int gof_slab_phase_sort_async(gof_engine* e, float timestep, void* st
                (const int*)(words + 1), e->cell_of, e->off, e->start, e->slot_id);
     GOF_LAUNCH(k_rank_gather_kick, cdiv(bound, kBinThreads), kBinThreads, 0, st, bound, (const int*)(words + 1),
                e->cell_of, e->start, e->count, e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1],
-               e->veli[1], e->cell_sorted, (float4*)nullptr, (float4*)nullptr, e->scalars, 1);
+               e->veli[1], e->cell_sorted, 0, e->scalars, 1);
     GOF_LAUNCH(k_slab_counts, 1, 1, 0, st, e->start, e->counters + 2, e->counters + 4, g.num_cells, g.nbx * g.nby,
                g.nlz - 2);
     e->n_slots = bound;  // upper bound until gof_slab_commit

@@ -260,10 +260,9 @@ constexpr float kDummyPos = 1e18f;  // a padding slot sits here: (1e18)^2 * 3 st
 
 // One thread per SOURCE particle (rest order): its rank among the ids of its cell is its
 // slot in the cell's segment.  `pstart` is the table the segments are laid out with: the
-// true starts, or the even-padded starts when `dup_a` is given.  In padded mode the last
-// particle of an odd cell also writes the dummy that fills the segment, and every particle
-// is written a second time in the duplicated layout {x, x, y, y} {z, z, type, 0} that the
-// packed (two homes per lane) force kernel streams.
+// true starts, or the even-padded starts (`padded`), in which case the last particle of an odd
+// cell also writes the dummy that fills the segment (the packed two-homes-per-lane force kernel
+// needs the two particles of a lane to share a cell).
 __global__ void __launch_bounds__(kBinThreads)
 k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict__ cell_of,
                    const int* __restrict__ pstart,
@@ -271,9 +270,8 @@ k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict
                    int sentinel_cell, const float4* __restrict__ posw_in,
                    const float4* __restrict__ veli_in, const float4* __restrict__ acc_in,
                    float4* __restrict__ posw_out, float4* __restrict__ veli_out,
-                   int* __restrict__ cell_sorted, float4* __restrict__ dup_a,
-                   float4* __restrict__ dup_b, const StepScalars* __restrict__ scalars,
-                   int apply_kick)
+                   int* __restrict__ cell_sorted, int padded,
+                   const StepScalars* __restrict__ scalars, int apply_kick)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_limit) n = min(n, *n_limit);
@@ -303,17 +301,12 @@ k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict
     posw_out[dst] = p;
     veli_out[dst] = v;
     cell_sorted[dst] = c;
-    if (dup_a) {
-        dup_a[dst] = make_float4(p.x, p.x, p.y, p.y);
-        dup_b[dst] = make_float4(p.z, p.z, p.w, 0.0f);
-        if (rank == cnt - 1 && (cnt & 1)) {
-            const float D = kDummyPos;
-            posw_out[dst + 1] = make_float4(D, D, D, __int_as_float(0));
-            veli_out[dst + 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            cell_sorted[dst + 1] = c;
-            dup_a[dst + 1] = make_float4(D, D, D, D);
-            dup_b[dst + 1] = make_float4(D, D, __int_as_float(0), 0.0f);
-        }
+    if (padded && rank == cnt - 1 && (cnt & 1)) {
+        // the padding slot of an odd cell: far away, type 0 (a valid table index), never a home
+        const float D = kDummyPos;
+        posw_out[dst + 1] = make_float4(D, D, D, __int_as_float(0));
+        veli_out[dst + 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        cell_sorted[dst + 1] = c;
     }
 }
 

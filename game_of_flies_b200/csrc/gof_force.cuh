@@ -17,10 +17,6 @@
 #pragma once
 #include "gof_binning.cuh"
 
-#ifndef GOF_FORCE_UNROLL8
-#define GOF_FORCE_UNROLL8 0
-#endif
-
 namespace gof {
 
 constexpr int kForceThreads = 128;
@@ -39,8 +35,6 @@ struct ForceArgs {
     const int* count;         // population of every cell
     const int* pstart;        // first slot of every cell in the snapshot the kernel reads
                               // (== start, or the even-padded table of the packed kernel)
-    const float4* dup_a;      // packed kernel only: {x, x, y, y} per snapshot slot
-    const float4* dup_b;      //                     {z, z, type bits, 0}
     int home_begin, home_count;
     // Optional second range (slab mode: the two boundary layers in one launch): threads
     // [0, home_count) cover home_begin.., threads [home_count, home_count + home_count2) cover
@@ -317,40 +311,6 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
     const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
     h.ax = h.ay = h.az = 0.0f;
     int j = s;
-#if GOF_FORCE_UNROLL8
-    if (!BOIDS) {
-        // eight loads in flight: most neighbour lines are first touched by this warp and come
-        // from L2 (~300 cycles); two groups of arithmetic cover that
-        for (; j + 8 <= e; j += 8) {
-            const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
-                         p3 = ldg4(a.posw + j + 3), p4 = ldg4(a.posw + j + 4), p5 = ldg4(a.posw + j + 5),
-                         p6 = ldg4(a.posw + j + 6), p7 = ldg4(a.posw + j + 7);
-            const float d0 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p0);
-            const float d1 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p1);
-            const float d2 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p2);
-            const float d3 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p3);
-            const float d4 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p4);
-            const float d5 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p5);
-            const float d6 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p6);
-            const float d7 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p7);
-            const bool band = (!(d0 < g.r2_lo) && d0 < g.r2_hi) | (!(d1 < g.r2_lo) && d1 < g.r2_hi) |
-                              (!(d2 < g.r2_lo) && d2 < g.r2_hi) | (!(d3 < g.r2_lo) && d3 < g.r2_hi) |
-                              (!(d4 < g.r2_lo) && d4 < g.r2_hi) | (!(d5 < g.r2_lo) && d5 < g.r2_hi) |
-                              (!(d6 < g.r2_lo) && d6 < g.r2_hi) | (!(d7 < g.r2_lo) && d7 < g.r2_hi);
-            const float lo8 = fminf(fminf(fminf(d0, d1), fminf(d2, d3)), fminf(fminf(d4, d5), fminf(d6, d7)));
-            if (band | (lo8 <= 1e-10f)) {
-                if (needs_repair(g, d0)) repair(h, tabrow, g, im, p0);
-                if (needs_repair(g, d1)) repair(h, tabrow, g, im, p1);
-                if (needs_repair(g, d2)) repair(h, tabrow, g, im, p2);
-                if (needs_repair(g, d3)) repair(h, tabrow, g, im, p3);
-                if (needs_repair(g, d4)) repair(h, tabrow, g, im, p4);
-                if (needs_repair(g, d5)) repair(h, tabrow, g, im, p5);
-                if (needs_repair(g, d6)) repair(h, tabrow, g, im, p6);
-                if (needs_repair(g, d7)) repair(h, tabrow, g, im, p7);
-            }
-        }
-    }
-#endif
     for (; j + 4 <= e; j += 4) {
         // four independent 16-byte loads issued ahead of the arithmetic that consumes them
         const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),

@@ -6,8 +6,9 @@
 // and the 128 B/clk return path from L1/shared to the register file (16 B of neighbour
 // + 24 B of species parameters per lane and pair).  Here a lane owns TWO consecutive
 // particles of the same cell, so that
-//   * every broadcast neighbour load (2 x 16 B, duplicated layout {x,x,y,y} {z,z,type,0})
-//     feeds two pairs: 16 B per lane and pair, and no register shuffling to form operands;
+//   * every broadcast neighbour load (one 16-byte {x,y,z,type}) feeds two pairs: 8 B per lane
+//     and pair through the L1 -> register path, which is what limits the one-home kernel
+//     (its test-only loop already takes 0.93 ms at 26 % issue utilisation);
 //   * separations, squared distances, profile and accumulation are one packed instruction
 //     for both pairs: ~15 issue slots per pair;
 //   * the species parameters live in registers and are reloaded only when the neighbour
@@ -123,14 +124,17 @@ __device__ __noinline__ float3 repair_pair2(const Geometry& g, float xi, float y
 template <bool LOWFIX>
 __device__ __forceinline__ float2 neighbour2(Home2& h, PackedParams& pp, const Derived& der,
                                              const Geometry& g, const Image2& im, float2 nmid2,
-                                             float hw2, const float4 A, const float4 B,
-                                             bool& band, float& dmin)
+                                             float hw2, const float4 P, bool& band, float& dmin)
 {
+    // One 16-byte neighbour {x, y, z, type} serves both home particles: the duplicated operands
+    // of the packed instructions are formed in registers (a few MOVs on an idle pipe), not
+    // loaded -- the L1 -> register return path (128 B/clk/SM, 512 B per broadcast LDG.128) is
+    // what limits this loop, not the issue slots.
     // neighbour - home (the force below is accumulated with the matching sign)
-    float2 dx = add2(f2(A.x, A.y), im.nx), dy = add2(f2(A.z, A.w), im.ny), dz = add2(f2(B.x, B.y), im.nz);
+    float2 dx = add2(f2(P.x, P.x), im.nx), dy = add2(f2(P.y, P.y), im.ny), dz = add2(f2(P.z, P.z), im.nz);
     if (LOWFIX) { dx = add2(dx, im.nlx); dy = add2(dy, im.nly); dz = add2(dz, im.nlz); }
     const float2 d2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, f2(kTinyD2, kTinyD2))));
-    const int tj = __float_as_int(B.z);
+    const int tj = __float_as_int(P.w);
     // neighbours are ordered by id inside a cell and ids are numbered species by species: the
     // type changes about once per six neighbours.  The vote makes this a real (mostly
     // not-taken) branch instead of a handful of predicated loads on every neighbour.
@@ -160,19 +164,18 @@ __device__ __forceinline__ bool needs_repair2(const Geometry& g, float2 d2)
 }
 
 __device__ __forceinline__ void repair2(Home2& h, const PairParam* __restrict__ tab, int T,
-                                        const Geometry& g, const Image2& im, const float4 A,
-                                        const float4 B, float2 d2)
+                                        const Geometry& g, const Image2& im, const float4 P, float2 d2)
 {
-    const int tj = __float_as_int(B.z);
+    const int tj = __float_as_int(P.w);
     if (needs_repair(g, d2.x)) {
         const float3 f = repair_pair2(g, h.x.x, h.y.x, h.z.x, im.nx.x, im.ny.x, im.nz.x, im.nlx.x,
-                                      im.nly.x, im.nlz.x, im.shifts, A.x, A.z, B.x, d2.x,
+                                      im.nly.x, im.nlz.x, im.shifts, P.x, P.y, P.z, d2.x,
                                       tab + h.t0 * T + tj);
         h.ax.x += f.x; h.ay.x += f.y; h.az.x += f.z;
     }
     if (needs_repair(g, d2.y)) {
         const float3 f = repair_pair2(g, h.x.y, h.y.y, h.z.y, im.nx.y, im.ny.y, im.nz.y, im.nlx.y,
-                                      im.nly.y, im.nlz.y, im.shifts, A.x, A.z, B.x, d2.y,
+                                      im.nly.y, im.nlz.y, im.shifts, P.x, P.y, P.z, d2.y,
                                       tab + h.t1 * T + tj);
         h.ax.y += f.x; h.ay.y += f.y; h.az.y += f.z;
     }
@@ -186,30 +189,33 @@ __device__ __forceinline__ void run_pairs2(Home2& h, PackedParams& pp, const Der
     // the run sums into its own accumulators (shorter partial sums: less fp32 rounding)
     const float2 ax0 = h.ax, ay0 = h.ay, az0 = h.az;
     h.ax = h.ay = h.az = f2(0.f, 0.f);
-    const float4* __restrict__ da = a.dup_a;
-    const float4* __restrict__ db = a.dup_b;
+    const float4* __restrict__ src = a.posw;  // padded snapshot {x, y, z, type}
     // centre and half width of the guard band [r2_lo, r2_hi) (a little wider: a false alarm only
     // costs a trip through the repair code, which decides exactly)
     const float mid = 0.5f * (g.r2_lo + g.r2_hi), hw2 = 0.51f * (g.r2_hi - g.r2_lo) + 1e-30f;
     const float2 nmid2 = f2(-mid, -mid);
     int j = s;
-    for (; j + 2 <= e; j += 2) {
-        const float4 A0 = ldg4(da + j), B0 = ldg4(db + j), A1 = ldg4(da + j + 1), B1 = ldg4(db + j + 1);
+    for (; j + 4 <= e; j += 4) {
+        const float4 P0 = ldg4(src + j), P1 = ldg4(src + j + 1), P2 = ldg4(src + j + 2), P3 = ldg4(src + j + 3);
         bool band = false;
         float dmin = 1.0f;
-        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, A0, B0, band, dmin);
-        const float2 d1 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, A1, B1, band, dmin);
+        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, P0, band, dmin);
+        const float2 d1 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, P1, band, dmin);
+        const float2 d2 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, P2, band, dmin);
+        const float2 d3 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, P3, band, dmin);
         if (band | (dmin <= 1e-10f)) {
-            if (needs_repair2(g, d0)) repair2(h, tab, der.T, g, im, A0, B0, d0);
-            if (needs_repair2(g, d1)) repair2(h, tab, der.T, g, im, A1, B1, d1);
+            if (needs_repair2(g, d0)) repair2(h, tab, der.T, g, im, P0, d0);
+            if (needs_repair2(g, d1)) repair2(h, tab, der.T, g, im, P1, d1);
+            if (needs_repair2(g, d2)) repair2(h, tab, der.T, g, im, P2, d2);
+            if (needs_repair2(g, d3)) repair2(h, tab, der.T, g, im, P3, d3);
         }
     }
-    if (j < e) {
-        const float4 A0 = ldg4(da + j), B0 = ldg4(db + j);
+    for (; j < e; ++j) {
+        const float4 P0 = ldg4(src + j);
         bool band = false;
         float dmin = 1.0f;
-        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, A0, B0, band, dmin);
-        if (needs_repair2(g, d0)) repair2(h, tab, der.T, g, im, A0, B0, d0);
+        const float2 d0 = neighbour2<LOWFIX>(h, pp, der, g, im, nmid2, hw2, P0, band, dmin);
+        if (needs_repair2(g, d0)) repair2(h, tab, der.T, g, im, P0, d0);
     }
     h.ax = add2(h.ax, ax0); h.ay = add2(h.ay, ay0); h.az = add2(h.az, az0);
 }
