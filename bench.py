@@ -173,7 +173,7 @@ def cpu_baseline(workload: str, seed: int, density, budget_s: float = 20.0):
     finishes in seconds.  particle-updates/s is intensive at fixed density."""
     from oracle import oracle as orc
     threads = orc.max_threads()
-    n_sample = 100_000
+    n_sample = 250_000
     hs = build_workload(workload, n_sample, seed, density)
     o = oracle_sim_from(hs, threads)
     o.core_step()  # warm-up (page faults, OpenMP pool)
@@ -183,7 +183,7 @@ def cpu_baseline(workload: str, seed: int, density, budget_s: float = 20.0):
         o.core_step()
         steps += 1
         el = time.perf_counter() - t0
-        if el > budget_s or steps >= 50:
+        if el > budget_s or steps >= 400:
             break
     return {"value": n_sample * steps / el, "unit": "particle-updates/s", "cores": threads,
             "kind": "port",

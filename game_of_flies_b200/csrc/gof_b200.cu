@@ -694,7 +694,7 @@ struct gof_engine {
     // carved from the arena
     size_t arena_bytes = 0;
     float4 *posw[2] = {nullptr, nullptr}, *veli[2] = {nullptr, nullptr}, *acc = nullptr;
-    int *cell_of = nullptr, *off = nullptr, *slot_id = nullptr, *slot_src = nullptr, *cell_sorted = nullptr;
+    int *cell_of = nullptr, *off = nullptr, *slot_id = nullptr, *cell_sorted = nullptr;
     int *count = nullptr, *start = nullptr, *pstart = nullptr, *tile_sums = nullptr;
     int slot_capacity = 0;                      // capacity + num_cells + 2 (even-padded segments)
     StepScalars* scalars = nullptr;
@@ -714,7 +714,6 @@ struct gof_engine {
     float4 *mig_recv[2] = {nullptr, nullptr};  // [0] from the slab below, [1] from above
     int* counters = nullptr;                   // [0..2] leavers down / up / error, [4..7] sort results
     int n_slots = 0;        // resident slots before the sort (live + dead + arrivals)
-    int n_halo[2] = {0, 0};
     int lo_pop = 0, hi_pop = 0;  // populations of the two owned boundary layers (gof_slab_commit)
 
     // optional per-launch timing of the force kernel (bench.py roofline)
@@ -748,7 +747,6 @@ static size_t engine_layout(gof_engine* e, char* base)
     e->cell_of = (int*)take(cap * sizeof(int));
     e->off = (int*)take(cap * sizeof(int));
     e->slot_id = (int*)take(slots * sizeof(int));
-    e->slot_src = (int*)take(16);
     e->cell_sorted = (int*)take(slots * sizeof(int));
     e->count = (int*)take(cells * sizeof(int));
     e->start = (int*)take(cells * sizeof(int));

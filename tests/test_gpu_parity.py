@@ -266,6 +266,27 @@ def test_engine_trajectory_statistics_against_oracle(gof):
     e.close()
 
 
+def test_long_run_stays_sane(gof):
+    """400 steps of a mixed Clusters+Boids box (clusters form, cells become very uneven): every
+    particle stays in the box, finite, ids remain a permutation, speeds respect the integrator's
+    clamp-then-half-kick bound, and the binning of the last step is consistent."""
+    st = random_state([2500] * 6, (100, 100, 100), seed=41, kinds="mixed", speed=3.0)
+    e = engine_from_state(gof, st)
+    e.step(400)
+    out = e.download(pos=True, vel=True, acc=True)
+    for k in ("pos", "vel", "acc"):
+        assert np.all(np.isfinite(out[k])), k
+    L = st["limits"][:, None]
+    assert np.all(out["pos"] >= 0) and np.all(out["pos"] <= L)
+    pb, cnt, stt, idx = e.read_bins()
+    assert cnt.sum() == st["n"] and np.array_equal(np.sort(idx), np.arange(st["n"]))
+    assert np.array_equal(stt, np.concatenate([[0], np.cumsum(cnt)[:-1]]))
+    assert cnt.max() > 3 * cnt.mean(), "the run should have clustered (uneven cells)"
+    # |v| <= 20 after step1; step2 adds a * dt / 2 with dt <= 0.4 / max|v| of the step before
+    assert np.linalg.norm(out["vel"], axis=0).max() < 60.0
+    e.close()
+
+
 def test_simulation_class_drop_in(gof, tmp_path):
     """The reference's Simulation surface: update(), output, update_parameter_matrix, blind_run + record."""
     from game_of_flies_b200.simulation import Simulation
