@@ -279,7 +279,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        from game_of_flies_b200.slab import nccl_options
+        dist.init_process_group("nccl", device_id=device, pg_options=nccl_options())
 
     def barrier():
         if world > 1:

@@ -218,7 +218,10 @@ class SlabEngine:
     def side_stream(self):
         """A second stream for the halo traffic that runs under the interior forces."""
         if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.index)
+            # HIGH priority: its few blocks (size gather, halo copies, boundary layers) must be
+            # scheduled ahead of the thousands of pending blocks of the interior kernel, otherwise
+            # they only start when that kernel drains and nothing overlaps
+            self._side = torch.cuda.Stream(device=self.index, priority=-1)
         return self._side
 
 
@@ -261,9 +264,19 @@ class LocalComm:
                     d.copy_(s, non_blocking=True)
 
 
+def nccl_options():
+    """Process-group options for the slab runner: NCCL's own stream at high priority, so that
+    the small halo / size messages are not queued behind the interior force kernel's blocks."""
+    import torch.distributed as dist
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return opts
+
+
 class DistComm:
     """One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests).
-    Slab s belongs to rank s * world / world_slabs (normally one slab per rank)."""
+    Slab s belongs to rank s * world / world_slabs (normally one slab per rank).  Create the
+    NCCL group with `pg_options=nccl_options()`."""
 
     def __init__(self, world_slabs: int, device=None):
         import torch.distributed as dist

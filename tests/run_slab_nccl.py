@@ -26,9 +26,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=device)
     from game_of_flies_b200.engine import ParticleEngine
-    from game_of_flies_b200.slab import DistComm, SlabEngine, SlabRunner, assign_to_slabs, split_layers
+    from game_of_flies_b200.slab import (DistComm, SlabEngine, SlabRunner, assign_to_slabs, nccl_options,
+                                         split_layers)
+    dist.init_process_group("nccl", device_id=device, pg_options=nccl_options())
 
     ok = True
     for kinds, counts, limits, speed, timestep in [
