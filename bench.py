@@ -233,7 +233,7 @@ def workload_config(args, hs, n_total, note=None):
                     f"r_max {float(hs['r_max']):.3f}, uniform random start, adaptive timestep",
         "particles_per_gpu": int(n_total // max(int(os.environ.get("WORLD_SIZE", "1")), 1)),
         "bins": [int(hs["num_bin_x"]), int(hs["num_bin_y"]), int(hs["num_bin_z"])],
-        "wrap_mode": "reference",
+        "wrap_mode": getattr(args, "wrap", "reference"),
         "cache": ("L2 flushed between timed steps (256 MiB overwrite outside the per-step event pairs)"
                   if getattr(args, "flush_l2", True) else "no L2 flush: per-step working set ~100 MB at N = 1M"),
     }
@@ -257,6 +257,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false",
                     help="do not overwrite a 256 MiB buffer between timed steps")
+    ap.add_argument("--wrap", default="reference", choices=["reference", "minimage"],
+                    help="periodic wrap semantics: the reference's (z-wrap quirk included) or minimum image")
     ap.add_argument("--packed", action="store_true", help="use the packed two-homes-per-lane Clusters kernel")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
@@ -290,6 +292,7 @@ def main():
     lib = _lib.load()
     n = args.particles
     cand = None
+    wrap_mode = _lib.WRAP_REFERENCE if args.wrap == "reference" else _lib.WRAP_MINIMAGE
     if world == 1:
         # ---- one GPU: the resident engine on the whole periodic box -------------------------
         hs = build_workload(args.workload, n, args.seed, args.density)
@@ -303,7 +306,7 @@ def main():
         o_vel = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
         o_acc = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
         eng = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), device=device,
-                             packed=args.packed)
+                             packed=args.packed, wrap_mode=wrap_mode)
         eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
         step = lambda k: eng.step(k)
 
@@ -344,7 +347,7 @@ def main():
         ids = np.arange(n, dtype=np.int32) + rank * n
         zeros = np.zeros((3, n), dtype=np.float32)
         eng = SlabEngine(hs["parameter_matrix"], limits, float(hs["r_max"]), lo, hi, capacity=int(1.3 * n) + 8192,
-                         device=device)
+                         device=device, wrap_mode=wrap_mode)
         eng.upload(pos, types, ids, vel=zeros, acc=zeros)
         runner = SlabRunner({rank: eng}, world, DistComm(world, device=device))
         step = lambda k: runner.step(k)

@@ -156,6 +156,18 @@ static int make_geometry(const gof_grid* grid, int layer_base, int local_layers,
     g.Ly = (float)g.Lyd;
     g.Lz = (float)g.Lzd;
     g.rmax = (float)g.rmaxd;
+    g.Lx_lo = (float)(g.Lxd - (double)g.Lx);
+    g.Ly_lo = (float)(g.Lyd - (double)g.Ly);
+    g.Lz_lo = (float)(g.Lzd - (double)g.Lz);
+    {
+        float r = (float)g.rmaxd;
+        if ((double)r < g.rmaxd) r = next_up(r);
+        g.zq_r = r;
+        const double top = g.Lzd - g.rmaxd;
+        float t = (float)top;
+        if ((double)t > top) t = next_down(t);
+        g.zq_top = t;
+    }
     // Guard band: the fp32 squared distance of a pair whose true distance is r_max can be
     // off by the rounding of the shifted coordinate (<= ulp(L + r_max)), the rounding of
     // the difference and of the three squares.  Inside the band the kernel decides in fp64.
@@ -309,7 +321,8 @@ static int launch_scan(const int* in, int m, int* tile_sums, int* out, cudaStrea
 
 static size_t force2_smem_bytes(int T)
 {
-    return (size_t)T * T * sizeof(PairParam) + (size_t)T * T * T * (2 * sizeof(float4) + sizeof(float2)) + 16;
+    return (size_t)T * T * sizeof(PairParam) + (size_t)T * T * T * (2 * sizeof(float4) + sizeof(float2)) +
+           (size_t)T * (T | 1) * (sizeof(float4) + sizeof(float2)) + 32;
 }
 
 // the packed two-homes-per-lane Clusters kernel; `slots` = upper bound of padded slots

@@ -156,25 +156,25 @@ struct Image {
     float x, y, z;     // rounded home + s * L
     float lx, ly, lz;  // exact remainder of that sum
     int shifts;        // packed (sx, sy, sz)
-    bool up;           // some axis was shifted upwards
+    bool up;           // some `lo` part is non-zero: the run needs the LOWFIX variant
 };
 
-__device__ __forceinline__ void shifted(float v, int s, float L, float& hi, float& lo)
+__device__ __forceinline__ void shifted(float v, int s, float L, float L_lo, float& hi, float& lo)
 {
     const float t = s * L;
     hi = v + t;
     const float bb = hi - v;
-    lo = (v - (hi - bb)) + (t - bb);
+    lo = (v - (hi - bb)) + (t - bb) + s * L_lo;  // + the part of the float64 limit that (float)L lost
 }
 
 __device__ __forceinline__ Image make_image(const Home& h, const Geometry& g, int sx, int sy, int sz)
 {
     Image im;
-    shifted(h.x, sx, g.Lx, im.x, im.lx);
-    shifted(h.y, sy, g.Ly, im.y, im.ly);
-    shifted(h.z, sz, g.Lz, im.z, im.lz);
+    shifted(h.x, sx, g.Lx, g.Lx_lo, im.x, im.lx);
+    shifted(h.y, sy, g.Ly, g.Ly_lo, im.y, im.ly);
+    shifted(h.z, sz, g.Lz, g.Lz_lo, im.z, im.lz);
     im.shifts = pack_shifts(sx, sy, sz);
-    im.up = (sx > 0) | (sy > 0) | (sz > 0);
+    im.up = (im.lx != 0.0f) | (im.ly != 0.0f) | (im.lz != 0.0f);  // some remainder to add per pair
     return im;
 }
 
@@ -370,55 +370,206 @@ __device__ __forceinline__ void run_image(Home& h, RowAddr tabrow_s,
 // cell (no x merging), with the comparisons in float64 like the reference.
 //   direct : the home particle is the reference's thread i, the neighbour its j
 //   !direct: the neighbour is thread i and updated the home particle as its j
+// z separation (home - neighbour) and the neighbour's relative z the reference accumulates
+// for cohesion, by the literal rules above, in fp32: the comparisons use the pre-rounded
+// thresholds (exactly the reference's float64 decisions) and every shift subtracts Lz from
+// the LARGER coordinate (exact), never adds it to the smaller one.
+__device__ __forceinline__ void quirk_dz(const Geometry& g, bool direct, float zi, float yi, float zj,
+                                         float yj, float& dz, float& relz)
+{
+    const bool i_low = zi < g.zq_r, j_low = zj < g.zq_r, i_top = zi > g.zq_top, j_top = zj > g.zq_top;
+    const float zi_m = (zi - g.Lz) - g.Lz_lo, zj_m = (zj - g.Lz) - g.Lz_lo;  // one box length down
+    if (direct) {
+        if (i_low && j_top) dz = zi - zj_m;                   // z2 = zj - Lz
+        else if (j_low && yi > g.zq_top) dz = zi_m - zj;     // z2 = zj + Lz   (the y test is the quirk)
+        else dz = zi - zj;
+        relz = -dz;
+    } else {
+        if (j_low && i_top) dz = zi_m - zj;                   // the neighbour moved the home: z2 = zi - Lz
+        else if (i_low && yj > g.zq_top) dz = zi - zj_m;     // z2 = zi + Lz
+        else dz = zi - zj;
+        if (i_low && j_top) relz = zj_m - zi;                 // ... and min-imaged ITS z towards the home
+        else if (j_low && i_top) relz = zj - zi_m;
+        else relz = zj - zi;
+    }
+}
+
+// float64 squared distance of a pair on the literal path (guard band / edge of r_sep)
+__device__ __noinline__ double quirk_exact_d2(const Geometry& g, bool direct, float hx, float hy, float hz,
+                                              float pjx, float pjy, float pjz, int sx, int sy)
+{
+    const double R = g.rmaxd, Lz = g.Lzd, top = g.Lzd - g.rmaxd;
+    const double zi = hz, zj = pjz;
+    double dzd;
+    if (direct) {
+        double z2 = zj;
+        if (zi < R && z2 > top) z2 -= Lz;
+        else if (z2 < R && (double)hy > top) z2 += Lz;
+        dzd = zi - z2;
+    } else {
+        double z2 = zi;
+        if (zj < R && z2 > top) z2 -= Lz;
+        else if (z2 < R && (double)pjy > top) z2 += Lz;
+        dzd = z2 - zj;
+    }
+    const double x2 = sx ? __dsub_rn((double)pjx, sx * g.Lxd) : (double)pjx;
+    const double y2 = sy ? __dsub_rn((double)pjy, sy * g.Lyd) : (double)pjy;
+    const double ddx = __dsub_rn((double)hx, x2), ddy = __dsub_rn((double)hy, y2);
+    return __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(dzd, dzd));
+}
+
+// Cold path of the literal Clusters loop (cf. repair_pair_clusters).
+__device__ __noinline__ float3 repair_quirk_clusters(const Geometry& g, bool direct, float hx, float hy,
+                                                     float hz, float pjx, float pjy, float pjz, int sx,
+                                                     int sy, float dx, float dy, float dz, float d2,
+                                                     const PairParam* q)
+{
+    const bool added = d2 < g.r2_lo;
+    const double e = quirk_exact_d2(g, direct, hx, hy, hz, pjx, pjy, pjz, sx, sy);
+    const bool wanted = (1e-10 < e) && (e < g.r2d);
+    if (added == wanted) return make_float3(0.f, 0.f, 0.f);
+    const float4 qa = q->a;
+    const float4 qb = q->b;
+    const float inv = fast_rsqrt(d2 + kTinyD2);
+    const float dist = d2 * inv;
+    const float f_in = fmaf(-qa.y, dist, qa.z);
+    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+    float s = (dist < qa.x ? f_in : f_tri) * inv;
+    if (added) s = -s;
+    return make_float3(-s * dx, -s * dy, -s * dz);
+}
+
 template <bool BOIDS>
-__device__ __noinline__ void run_pairs_zquirk(Home& h, const PairParam* __restrict__ tabrow,
+__device__ __forceinline__ void quirk_pair(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
+                                           float* __restrict__ boid_acc, const ForceArgs& a,
+                                           const Geometry& g, const Image& im, int sx, int sy, bool direct,
+                                           int j, const float4 pj)
+{
+    float dz, relz;
+    quirk_dz(g, direct, h.z, h.y, pj.z, pj.y, dz, relz);
+    const float dx = (im.x - pj.x) + im.lx, dy = (im.y - pj.y) + im.ly;
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (!BOIDS) {
+        // branch-free like pair_clusters: force for every candidate, masked by the cut-off
+        const unsigned tj = (unsigned)__float_as_int(pj.w);
+        const float4 qa = lds4(tabrow_s.a + tj * 16u);
+        const float2 qb = lds2(tabrow_s.b + tj * 8u);
+        const float inv = fast_rsqrt(d2 + kTinyD2);
+        const float dist = d2 * inv;
+        const float f_in = fmaf(-qa.y, dist, qa.z);
+        const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+        float s = (dist < qa.x ? f_in : f_tri) * inv;
+        s = d2 < g.r2_lo ? s : 0.0f;
+        h.ax = fmaf(-s, dx, h.ax);
+        h.ay = fmaf(-s, dy, h.ay);
+        h.az = fmaf(-s, dz, h.az);
+        if (needs_repair(g, d2)) {
+            const float3 f = repair_quirk_clusters(g, direct, h.x, h.y, h.z, pj.x, pj.y, pj.z, sx, sy, dx, dy,
+                                                   dz, d2, tabrow + tj);
+            h.ax += f.x; h.ay += f.y; h.az += f.z;
+        }
+    } else if (d2 < g.r2_hi && d2 > 1e-10f) {
+        const float hx = h.x, hy = h.y, hz = h.z;
+        auto exact = [&]() { return quirk_exact_d2(g, direct, hx, hy, hz, pj.x, pj.y, pj.z, sx, sy); };
+        bool ok = true;
+        if (d2 > g.r2_lo) {
+            const double d2d = exact();
+            ok = (1e-10 < d2d) && (d2d < g.r2d);
+        }
+        if (ok)
+            interact<BOIDS>(h, tabrow, boid_acc, a, a.T, j, __float_as_int(pj.w), dx, dy, dz, -dx, -dy, relz,
+                            d2, exact);
+    }
+}
+
+template <bool BOIDS>
+__device__ __forceinline__ void run_pairs_zquirk(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
                                               float* __restrict__ boid_acc, const ForceArgs& a,
                                               const Geometry& g, int s, int e, int sx, int sy,
                                               bool direct)
 {
     const Image im = make_image(h, g, sx, sy, 0);
-    const double R = g.rmaxd, Lz = g.Lzd, top = g.Lzd - g.rmaxd;
-    for (int j = s; j < e; ++j) {
-        const float4 pj = ldg4(a.posw + j);
-        const double zi = h.z, zj = pj.z;
-        double dzd, relz;
-        if (direct) {
-            double z2 = zj;
-            if (zi < R && z2 > top) z2 -= Lz;
-            else if (z2 < R && (double)h.y > top) z2 += Lz;
-            dzd = zi - z2;
-            relz = z2 - zi;
-        } else {
-            double z2 = zi;  // the neighbour (thread i) wraps the home particle (its j)
-            if (zj < R && z2 > top) z2 -= Lz;
-            else if (z2 < R && (double)pj.y > top) z2 += Lz;
-            dzd = z2 - zj;
-            double zw = zj;  // ... and accumulates ITS position min-imaged towards the home particle
-            if (zi < R && zw > top) zw -= Lz;
-            else if (zw < R && zi > top) zw += Lz;
-            relz = zw - zi;
+    int j = s;
+    for (; j + 4 <= e; j += 4) {
+        const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
+                     p3 = ldg4(a.posw + j + 3);
+        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j, p0);
+        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 1, p1);
+        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 2, p2);
+        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 3, p3);
+    }
+    for (; j < e; ++j)
+        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j, ldg4(a.posw + j));
+}
+
+// The whole stencil of ONE home particle on the literal path, out of line: the fast path of the
+// kernel keeps its own register allocation, and an edge-layer lane pays one call.
+// Same run structure and partial sums as the fast path (per row: the un-shifted x cells in
+// ascending order, then the cell across the x boundary), so that a particle's result does not
+// depend on which path its warp-mates take.
+template <bool BOIDS>
+__device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type, unsigned kinds,
+                                          RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
+                                          float* __restrict__ boid_acc, const ForceArgs& a,
+                                          const Geometry& g, int cx, int cy, int lz, int gz, bool valid)
+{
+    Home h;
+    h.x = hx; h.y = hy; h.z = hz;
+    h.vx = h.vy = h.vz = 0.0f;
+    h.ax = h.ay = h.az = 0.0f;
+    h.type = type;
+    h.kinds = kinds;
+    const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
+    for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
+        int nl = lz + dzi;
+        const int ngz = gz + dzi;
+        if (g.index_wrap_z) {
+            if (ngz < 0) nl += g.nbz;
+            else if (ngz >= g.nbz) nl -= g.nbz;
         }
-        const float dx = (im.x - pj.x) + im.lx, dy = (im.y - pj.y) + im.ly, dz = (float)dzd;
-        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d2 < g.r2_hi && d2 > 1e-10f) {
-            const float hx = h.x, hy = h.y, pjx = pj.x, pjy = pj.y;
-            auto exact = [&]() {
-                const double x2 = sx ? __dsub_rn((double)pjx, sx * g.Lxd) : (double)pjx;
-                const double y2 = sy ? __dsub_rn((double)pjy, sy * g.Lyd) : (double)pjy;
-                const double ddx = __dsub_rn((double)hx, x2), ddy = __dsub_rn((double)hy, y2);
-                return __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
-                                 __dmul_rn(dzd, dzd));
-            };
-            bool ok = true;
-            if (d2 > g.r2_lo) {
-                const double d2d = exact();
-                ok = (1e-10 < d2d) && (d2d < g.r2d);
+        for (int dyi = -1; dyi <= 1; ++dyi) {
+            int ny = cy + dyi, sy = 0;
+            if (ny < 0) { ny += g.nby; sy = 1; }
+            else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
+            const int rb = (nl * g.nby + ny) * g.nbx;
+            const int lo = cx > 0 ? cx - 1 : 0;
+            const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
+            float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+            h.ax = h.ay = h.az = 0.0f;
+            // Half stencil of set_bin_neighbours (acceleration_updater.py:140-215): the home particle
+            // is the reference's thread i ("direct") for the upper layer, for the row above in its own
+            // layer, and for its own cell and the next one in x; elsewhere the neighbour is.  Only the
+            // home row (dz = dy = 0) mixes the two, so every other row is one contiguous run.
+            if (dzi == 0 && dyi == 0) {
+                if (lo < cx) {
+                    const int s = a.pstart[rb + lo];
+                    const int e = valid ? s + a.count[rb + lo] : s;
+                    run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, false);
+                }
+                const int s = a.pstart[rb + cx];
+                const int e = valid ? a.pstart[rb + hi] + a.count[rb + hi] : s;
+                run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, true);
+            } else {
+                const bool direct = dzi == 1 || (dzi == 0 && dyi == 1);
+                const int s = a.pstart[rb + lo];
+                const int e = valid ? a.pstart[rb + hi] + a.count[rb + hi] : s;
+                run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, direct);
             }
-            if (ok)
-                interact<BOIDS>(h, tabrow, boid_acc, a, a.T, j, __float_as_int(pj.w), dx, dy, dz,
-                                -dx, -dy, (float)relz, d2, exact);
+            h.ax += ax0; h.ay += ay0; h.az += az0;
+            ax0 = h.ax; ay0 = h.ay; az0 = h.az;
+            h.ax = h.ay = h.az = 0.0f;
+            if (cx == 0 || cx == g.nbx - 1) {
+                const int wc = cx == 0 ? g.nbx - 1 : 0;
+                const int dxi = cx == 0 ? -1 : 1;
+                const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
+                const int s = a.pstart[rb + wc];
+                const int e = valid ? s + a.count[rb + wc] : s;
+                run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, cx == 0 ? 1 : -1, sy, direct);
+            }
+            h.ax += ax0; h.ay += ay0; h.az += az0;
         }
     }
+    return make_float3(h.ax, h.ay, h.az);
 }
 
 template <bool BOIDS, int MODE>
@@ -454,7 +605,16 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
         home_count = live - lo - hi;
         if (home_count <= 0) return;  // (block-uniform: one or two owned layers)
     }
-    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    // Block -> particles mapping, rotated so that the blocks of the TOP z layer run first, then the
+    // bottom layer, then the rest: in GOF_WRAP_REFERENCE mode those two layers take the literal path
+    // (~3x the work per particle) and would otherwise sit at the very end of the grid, stretching
+    // the kernel's tail.  (Single periodic box only: a slab launches its boundary layers apart.)
+    int first_block = 0;
+    if (g.is3d && g.index_wrap_z && a.wrap_mode == kWrapReference && a.home_count2 == 0 && !a.interior_words)
+        first_block = (a.pstart[(g.nlz - 1) * g.nbx * g.nby] - home_begin) / (int)blockDim.x;
+    int blk = (int)blockIdx.x + first_block;
+    if (blk >= (int)gridDim.x) blk -= (int)gridDim.x;
+    const int local = blk * blockDim.x + threadIdx.x;
     if (a.interior_words && local - (int)threadIdx.x >= home_count) return;  // whole block past the range
     const bool valid = local < home_count + a.home_count2;
     int k = home_begin + (local < home_count ? local : home_count - 1);
@@ -518,47 +678,9 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
             }
         }
     } else {
-        for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
-            int nl = lz + dzi;
-            const int ngz = gz + dzi;
-            if (g.index_wrap_z) {
-                if (ngz < 0) nl += g.nbz;
-                else if (ngz >= g.nbz) nl -= g.nbz;
-            }
-            for (int dyi = -1; dyi <= 1; ++dyi) {
-                int ny = cy + dyi, sy = 0;
-                if (ny < 0) { ny += g.nby; sy = 1; }
-                else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
-                const int rb = (nl * g.nby + ny) * g.nbx;
-                // Same run structure and partial sums as the fast path (the un-shifted x cells
-                // in ascending order, then the cell across the x boundary), so that a particle's
-                // result does not depend on which path its warp-mates forced it through.
-                const int lo = cx > 0 ? cx - 1 : 0;
-                const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
-                float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
-                h.ax = h.ay = h.az = 0.0f;
-                for (int nx = lo; nx <= hi; ++nx) {
-                    const int dxi = nx - cx;
-                    // half stencil of set_bin_neighbours (acceleration_updater.py:140-215)
-                    const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
-                    const int s = a.pstart[rb + nx];
-                    const int e = valid ? s + a.count[rb + nx] : s;
-                    run_pairs_zquirk<BOIDS>(h, tabrow, boid_acc, a, g, s, e, 0, sy, direct);
-                }
-                h.ax += ax0; h.ay += ay0; h.az += az0;
-                ax0 = h.ax; ay0 = h.ay; az0 = h.az;
-                h.ax = h.ay = h.az = 0.0f;
-                if (cx == 0 || cx == g.nbx - 1) {
-                    const int wc = cx == 0 ? g.nbx - 1 : 0;
-                    const int dxi = cx == 0 ? -1 : 1;
-                    const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
-                    const int s = a.pstart[rb + wc];
-                    const int e = valid ? s + a.count[rb + wc] : s;
-                    run_pairs_zquirk<BOIDS>(h, tabrow, boid_acc, a, g, s, e, cx == 0 ? 1 : -1, sy, direct);
-                }
-                h.ax += ax0; h.ay += ay0; h.az += az0;
-            }
-        }
+        const float3 f = quirk_home<BOIDS>(h.x, h.y, h.z, h.type, h.kinds, tabrow_s, tabrow, boid_acc, a, g, cx, cy,
+                                           lz, gz, valid);
+        h.ax = f.x; h.ay = f.y; h.az = f.z;
     }
 
     // ---- cohesion and alignment from the per-type means (acceleration_updater.py:422-458) ----

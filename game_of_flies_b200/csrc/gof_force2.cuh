@@ -83,14 +83,15 @@ __device__ __forceinline__ Image2 make_image2(const Home2& h, const Geometry& g,
 {
     Image2 im;
     float hi, lo;
-    shifted(h.x.x, sx, g.Lx, hi, lo); im.nx.x = -hi; im.nlx.x = -lo;
-    shifted(h.x.y, sx, g.Lx, hi, lo); im.nx.y = -hi; im.nlx.y = -lo;
-    shifted(h.y.x, sy, g.Ly, hi, lo); im.ny.x = -hi; im.nly.x = -lo;
-    shifted(h.y.y, sy, g.Ly, hi, lo); im.ny.y = -hi; im.nly.y = -lo;
-    shifted(h.z.x, sz, g.Lz, hi, lo); im.nz.x = -hi; im.nlz.x = -lo;
-    shifted(h.z.y, sz, g.Lz, hi, lo); im.nz.y = -hi; im.nlz.y = -lo;
+    shifted(h.x.x, sx, g.Lx, g.Lx_lo, hi, lo); im.nx.x = -hi; im.nlx.x = -lo;
+    shifted(h.x.y, sx, g.Lx, g.Lx_lo, hi, lo); im.nx.y = -hi; im.nlx.y = -lo;
+    shifted(h.y.x, sy, g.Ly, g.Ly_lo, hi, lo); im.ny.x = -hi; im.nly.x = -lo;
+    shifted(h.y.y, sy, g.Ly, g.Ly_lo, hi, lo); im.ny.y = -hi; im.nly.y = -lo;
+    shifted(h.z.x, sz, g.Lz, g.Lz_lo, hi, lo); im.nz.x = -hi; im.nlz.x = -lo;
+    shifted(h.z.y, sz, g.Lz, g.Lz_lo, hi, lo); im.nz.y = -hi; im.nlz.y = -lo;
     im.shifts = pack_shifts(sx, sy, sz);
-    im.up = (sx > 0) | (sy > 0) | (sz > 0);
+    im.up = (im.nlx.x != 0.0f) | (im.nlx.y != 0.0f) | (im.nly.x != 0.0f) | (im.nly.y != 0.0f) |
+            (im.nlz.x != 0.0f) | (im.nlz.y != 0.0f);
     return im;
 }
 
@@ -244,7 +245,17 @@ k_force2(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a
     float4* q0 = reinterpret_cast<float4*>(tab + T * T);
     float4* q1 = q0 + T * T * T;
     float2* q2 = reinterpret_cast<float2*>(q1 + T * T * T);
-    for (int q = threadIdx.x; q < T * T; q += blockDim.x) tab[q] = a.table[q];
+    // split tables of the one-home code (literal z-wrap path of the edge layers)
+    const int TA = T | 1;
+    float4* tabA = reinterpret_cast<float4*>(q2 + T * T * T + (T * T * T & 1));
+    float2* tabB = reinterpret_cast<float2*>(tabA + T * TA);
+    for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
+        const PairParam pp = a.table[q];
+        tab[q] = pp;
+        const int r = q / T, c = q - r * T;
+        tabA[r * TA + c] = pp.a;
+        tabB[r * TA + c] = make_float2(pp.b.x, pp.b.y);
+    }
     for (int q = threadIdx.x; q < T * T * T; q += blockDim.x) {
         const int tj = q % T, t1 = (q / T) % T, t0 = q / (T * T);
         // clusters: a = {r_min, k0, f_min, mid}, b = {s1, f_max}
@@ -325,53 +336,15 @@ k_force2(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a
         // one-home kernel, once per home particle (gof_force.cuh run_pairs_zquirk)
         for (int which = 0; which < 2; ++which) {
             const bool valid = which ? valid1 : valid0;
-            Home hs;
-            hs.x = which ? h.x.y : h.x.x; hs.y = which ? h.y.y : h.y.x; hs.z = which ? h.z.y : h.z.x;
-            hs.vx = hs.vy = hs.vz = 0.f;
-            hs.ax = hs.ay = hs.az = 0.f;
-            hs.type = which ? h.t1 : h.t0;
-            hs.kinds = 0u;
-            const PairParam* tabrow = tab + hs.type * T;
-            for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
-                int nl = lz + dzi;
-                const int ngz = gz + dzi;
-                if (g.index_wrap_z) {
-                    if (ngz < 0) nl += g.nbz;
-                    else if (ngz >= g.nbz) nl -= g.nbz;
-                }
-                for (int dyi = -1; dyi <= 1; ++dyi) {
-                    int ny = cy + dyi, sy = 0;
-                    if (ny < 0) { ny += g.nby; sy = 1; }
-                    else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
-                    const int rb = (nl * g.nby + ny) * g.nbx;
-                    // same run structure and partial sums as the fast path
-                    const int lo = cx > 0 ? cx - 1 : 0;
-                    const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
-                    float ax0 = hs.ax, ay0 = hs.ay, az0 = hs.az;
-                    hs.ax = hs.ay = hs.az = 0.0f;
-                    for (int nx = lo; nx <= hi; ++nx) {
-                        const int dxi = nx - cx;
-                        const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
-                        const int s = a.pstart[rb + nx];
-                        const int e = valid ? s + a.count[rb + nx] : s;
-                        run_pairs_zquirk<false>(hs, tabrow, nullptr, a, g, s, e, 0, sy, direct);
-                    }
-                    hs.ax += ax0; hs.ay += ay0; hs.az += az0;
-                    ax0 = hs.ax; ay0 = hs.ay; az0 = hs.az;
-                    hs.ax = hs.ay = hs.az = 0.0f;
-                    if (cx == 0 || cx == g.nbx - 1) {
-                        const int wc = cx == 0 ? g.nbx - 1 : 0;
-                        const int dxi = cx == 0 ? -1 : 1;
-                        const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
-                        const int s = a.pstart[rb + wc];
-                        const int e = valid ? s + a.count[rb + wc] : s;
-                        run_pairs_zquirk<false>(hs, tabrow, nullptr, a, g, s, e, cx == 0 ? 1 : -1, sy, direct);
-                    }
-                    hs.ax += ax0; hs.ay += ay0; hs.az += az0;
-                }
-            }
-            if (which) { h.ax.y = hs.ax; h.ay.y = hs.ay; h.az.y = hs.az; }
-            else       { h.ax.x = hs.ax; h.ay.x = hs.ay; h.az.x = hs.az; }
+            const int type = which ? h.t1 : h.t0;
+            RowAddr tabrow_s;
+            tabrow_s.a = (unsigned)__cvta_generic_to_shared(tabA + type * TA);
+            tabrow_s.b = (unsigned)__cvta_generic_to_shared(tabB + type * TA);
+            const float3 f = quirk_home<false>(which ? h.x.y : h.x.x, which ? h.y.y : h.y.x, which ? h.z.y : h.z.x,
+                                               type, 0u, tabrow_s, tab + type * T, nullptr, a, g, cx, cy, lz, gz,
+                                               valid);
+            if (which) { h.ax.y = f.x; h.ay.y = f.y; h.az.y = f.z; }
+            else       { h.ax.x = f.x; h.ay.x = f.y; h.az.x = f.z; }
         }
     }
 

@@ -47,7 +47,13 @@ struct Geometry {
     double bsx, bsy, bsz;  // bin sizes, float64 like the reference
     double Lxd, Lyd, Lzd, rmaxd, r2d;
     float Lx, Ly, Lz, rmax;
+    float Lx_lo, Ly_lo, Lz_lo;  // what (float)L lost: L = L + L_lo to ~2^-48 (exact periodic images)
     float r2_lo, r2_hi;  // guard band around r_max^2: inside it the cut-off is re-decided in float64
+    // thresholds of the reference's z-wrap tests, pre-rounded so that fp32 comparisons of fp32
+    // coordinates decide exactly like the reference's float64 ones:
+    //   z < r_max  <=>  z < zq_r     (zq_r   = smallest float >= r_max)
+    //   z > Lz - r_max  <=>  z > zq_top  (zq_top = largest float <= Lz - r_max)
+    float zq_r, zq_top;
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
