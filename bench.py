@@ -261,6 +261,8 @@ def main():
                     help="periodic wrap semantics: the reference's (z-wrap quirk included) or minimum image")
     ap.add_argument("--packed", action="store_true", help="use the packed two-homes-per-lane Clusters kernel")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--force-split", type=int, default=-1, choices=(-1, 1, 3, 9),
+                    help="warps per home particle in the small-system force kernel (-1: automatic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -290,6 +292,7 @@ def main():
         torch.cuda.synchronize(device)
 
     lib = _lib.load()
+    _lib.check(lib.gof_set_force_split(args.force_split))
     n = args.particles
     cand = None
     wrap_mode = _lib.WRAP_REFERENCE if args.wrap == "reference" else _lib.WRAP_MINIMAGE

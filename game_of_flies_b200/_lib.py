@@ -74,6 +74,8 @@ SIGNATURES = {
     "gof_engine_snapshot_copy": (_i, [_vp, _vp, _vp]),
     "gof_engine_read_bins": (_i, [_vp] + [_vp] * 4 + [_vp]),
     "gof_engine_set_kernel": (_i, [_vp, _i]),
+    "gof_set_force_split": (_i, [_i]),
+    "gof_engine_set_graph": (_i, [_vp, _i]),
     "gof_engine_timing": (_i, [_vp, _i]),
     "gof_engine_force_time": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
     "gof_engine_last_timestep": (_i, [_vp, C.POINTER(_f), _vp]),

@@ -273,34 +273,70 @@ static int upload_species(const HostSpecies& h, const DeviceSpecies& d, cudaStre
     return 0;
 }
 
-static size_t force_smem_bytes(int T, bool boids)
+static size_t force_smem_bytes(int T, bool boids, int split)
 {
     const size_t TA = (size_t)(T | 1);
     return (size_t)T * T * sizeof(PairParam) + (size_t)T * TA * (sizeof(float4) + sizeof(float2)) + 16 +
-           (boids ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0);
+           (boids ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0) +
+           (split > 1 ? (size_t)kSplitRuns * 3 * kSplitHomes * sizeof(float) : 0);
 }
 
-template <bool BOIDS, int MODE>
+template <bool BOIDS, int MODE, int SPLIT>
 static int launch_force_t(const Geometry& g, const ForceArgs& a, cudaStream_t st)
 {
-    const size_t smem = force_smem_bytes(a.T, BOIDS);
+    const size_t smem = force_smem_bytes(a.T, BOIDS, SPLIT);
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
-        GOF_CUDA(cudaFuncSetAttribute(k_force<BOIDS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        GOF_CUDA(cudaFuncSetAttribute(k_force<BOIDS, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      100 * 1024));
         attr_set = true;
     }
-    GOF_LAUNCH((k_force<BOIDS, MODE>), cdiv(a.home_count + a.home_count2, kForceThreads), kForceThreads, smem, st,
-               g, a);
+    const int homes = SPLIT == 1 ? kForceThreads : kSplitHomes;
+    GOF_LAUNCH((k_force<BOIDS, MODE, SPLIT>), cdiv(a.home_count + a.home_count2, homes), homes * SPLIT, smem, st, g, a);
     return 0;
+}
+
+// How many warps share one home particle's stencil (k_force's SPLIT).  Small Clusters-kind
+// systems are latency-bound with one thread per particle: split the 9 (3 in 2D) stencil rows over
+// warps while the launch still fits the GPU a few times over.  Results do not depend on it.
+static int g_force_split = -1;  // -1: automatic
+static constexpr int kResidentWarps = 148 * 20;
+
+static int pick_split(const Geometry& g, int homes, bool boids)
+{
+    if (boids) return 1;
+    if (g_force_split > 0) return (!g.is3d && g_force_split == 9) ? 3 : g_force_split;
+    const long warps = cdiv(homes, 32);
+    if (g.is3d && warps * 9 <= 3L * kResidentWarps) return 9;
+    if (warps * 3 <= 4L * kResidentWarps) return 3;
+    return 1;
+}
+
+extern "C" int gof_set_force_split(int split)
+{
+    if (split != -1 && split != 1 && split != 3 && split != 9)
+        return fail(GOF_E_INVALID, "gof_set_force_split: expected -1 (automatic), 1, 3 or 9");
+    g_force_split = split;
+    return 0;
+}
+
+template <int MODE>
+static int launch_force_m(const Geometry& g, const ForceArgs& a, bool boids, cudaStream_t st)
+{
+    if (boids) return launch_force_t<true, MODE, 1>(g, a, st);
+    switch (pick_split(g, a.home_count + a.home_count2, false)) {
+        case 9: return launch_force_t<false, MODE, 9>(g, a, st);
+        case 3: return launch_force_t<false, MODE, 3>(g, a, st);
+        default: return launch_force_t<false, MODE, 1>(g, a, st);
+    }
 }
 
 // a.home_count is the number of threads to launch (an upper bound when a.interior_words is set)
 static int launch_force(const Geometry& g, const ForceArgs& a, bool boids, int mode, cudaStream_t st)
 {
     if (a.home_count + a.home_count2 <= 0) return 0;
-    if (mode == kModeIntegrate)
-        return boids ? launch_force_t<true, kModeIntegrate>(g, a, st) : launch_force_t<false, kModeIntegrate>(g, a, st);
-    return boids ? launch_force_t<true, kModeScatter>(g, a, st) : launch_force_t<false, kModeScatter>(g, a, st);
+    if (mode == kModeIntegrate) return launch_force_m<kModeIntegrate>(g, a, boids, st);
+    return launch_force_m<kModeScatter>(g, a, boids, st);
 }
 
 // exclusive scan of m ints (PAD2: of the counts rounded up to even); tile_sums needs
@@ -729,6 +765,18 @@ struct gof_engine {
     int n_slots = 0;        // resident slots before the sort (live + dead + arrivals)
     int lo_pop = 0, hi_pop = 0;  // populations of the two owned boundary layers (gof_slab_commit)
 
+    // One core_step captured as a CUDA graph per parity (8 kernels + a memset become one launch;
+    // small systems are launch-bound).  Re-captured when anything baked into the nodes changes.
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        float timestep = 0.f;
+        int wrap_mode = 0, split = 0, generation = -1, launches = 0;
+        bool packed = false;
+    } graphs[2];
+    bool use_graph = true;
+    int generation = 0;             // bumped by whatever invalidates captured graphs
+    cudaStream_t capture_stream = nullptr;
+
     // optional per-launch timing of the force kernel (bench.py roofline)
     bool timing = false;
     std::vector<cudaEvent_t> ev;  // pairs: start, stop
@@ -807,8 +855,19 @@ extern "C" int gof_engine_create(gof_engine** out, int device, int num_particles
 extern "C" void gof_engine_destroy(gof_engine* e)
 {
     if (!e) return;
+    cudaSetDevice(e->device);
     for (cudaEvent_t v : e->ev) cudaEventDestroy(v);
+    for (auto& g : e->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     delete e;
+}
+
+extern "C" int gof_engine_set_graph(gof_engine* e, int enable)
+{
+    if (!e) return fail(GOF_E_INVALID, "null engine");
+    e->use_graph = enable != 0;
+    return 0;
 }
 
 extern "C" int gof_engine_set_kernel(gof_engine* e, int kernel)
@@ -818,6 +877,7 @@ extern "C" int gof_engine_set_kernel(gof_engine* e, int kernel)
         return fail(GOF_E_INVALID, "gof_engine_set_kernel: unknown kernel");
     e->want_packed = kernel == GOF_KERNEL_PACKED;
     e->binned = false;
+    ++e->generation;
     return 0;
 }
 
@@ -858,6 +918,7 @@ extern "C" int gof_engine_bind_arena(gof_engine* e, void* d_arena, size_t bytes)
     e->bound = true;
     e->uploaded = e->binned = false;
     e->species_dirty = true;
+    ++e->generation;
     return 0;
 }
 
@@ -866,6 +927,7 @@ extern "C" int gof_engine_set_parameters(gof_engine* e, const double* pm_host, v
     if (!e) return fail(GOF_E_INVALID, "null engine");
     if (int rc = build_species(pm_host, e->T, &e->species)) return rc;
     e->species_dirty = true;
+    ++e->generation;  // the kinds decide which kernel instantiation a step launches
     if (e->bound) {
         GOF_CUDA(cudaSetDevice(e->device));
         if (int rc = upload_species(e->species, e->dspecies, (cudaStream_t)stream)) return rc;
@@ -978,6 +1040,68 @@ static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
     a->n_total = e->n;
 }
 
+// the launches of one core_step at the engine's current parity (which the caller flips)
+static int engine_enqueue_step(gof_engine* e, float timestep, int wrap_mode, cudaStream_t st, bool timed)
+{
+    GOF_LAUNCH(k_prepare_dt, 1, 1, 0, st, e->scalars, e->parity, timestep < 0 ? -1.0f : timestep);
+    if (int rc = engine_bin(e, true, st)) return rc;
+    ForceArgs a;
+    engine_force_args(e, wrap_mode, &a);
+    a.integrate = 1;
+    a.parity_out = e->parity ^ 1;
+    if (timed) {
+        while ((int)e->ev.size() < 2 * (e->ev_used + 1)) {
+            cudaEvent_t v;
+            GOF_CUDA(cudaEventCreate(&v));
+            e->ev.push_back(v);
+        }
+        GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used], st));
+    }
+    if (int rc = engine_force(e, a, st)) return rc;
+    if (timed) {
+        GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used + 1], st));
+        ++e->ev_used;
+    }
+    return 0;
+}
+
+// (Re)capture the step at the current parity.  Captured on the engine's own stream, so that the
+// caller's stream may be the legacy default stream (which cannot be captured).
+static int engine_capture_step(gof_engine* e, float timestep, int wrap_mode)
+{
+    gof_engine::StepGraph& sg = e->graphs[e->parity];
+    if (sg.exec) {
+        cudaGraphExecDestroy(sg.exec);
+        sg.exec = nullptr;
+    }
+    if (!e->capture_stream) GOF_CUDA(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+    const uint64_t before = g_launches.load();
+    GOF_CUDA(cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = engine_enqueue_step(e, timestep, wrap_mode, e->capture_stream, false);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end = cudaStreamEndCapture(e->capture_stream, &graph);
+    const int launches = (int)(g_launches.load() - before);
+    g_launches.store(before);  // captured, not launched
+    if (rc || end != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc ? rc : fail((int)end, std::string("step capture: ") + cudaGetErrorString(end));
+    }
+    const cudaError_t inst = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) {
+        sg.exec = nullptr;
+        return fail((int)inst, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(inst));
+    }
+    sg.timestep = timestep;
+    sg.wrap_mode = wrap_mode;
+    sg.split = g_force_split;
+    sg.packed = engine_packed(e);
+    sg.generation = e->generation;
+    sg.launches = launches;
+    return 0;
+}
+
 extern "C" int gof_engine_step(gof_engine* e, int n_steps, float timestep, int wrap_mode, void* stream)
 {
     if (int rc = engine_ready(e, true)) return rc;
@@ -986,25 +1110,18 @@ extern "C" int gof_engine_step(gof_engine* e, int n_steps, float timestep, int w
     if (timestep == 0.0f || timestep != timestep) return fail(GOF_E_INVALID, "gof_engine_step: bad timestep");
     cudaStream_t st = (cudaStream_t)stream;
     for (int s = 0; s < n_steps; ++s) {
-        GOF_LAUNCH(k_prepare_dt, 1, 1, 0, st, e->scalars, e->parity, timestep < 0 ? -1.0f : timestep);
-        if (int rc = engine_bin(e, true, st)) return rc;
-        ForceArgs a;
-        engine_force_args(e, wrap_mode, &a);
-        a.integrate = 1;
-        a.parity_out = e->parity ^ 1;
         const bool timed = e->timing && e->ev_used < kMaxTimedLaunches;
-        if (timed) {
-            while ((int)e->ev.size() < 2 * (e->ev_used + 1)) {
-                cudaEvent_t v;
-                GOF_CUDA(cudaEventCreate(&v));
-                e->ev.push_back(v);
-            }
-            GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used], st));
-        }
-        if (int rc = engine_force(e, a, st)) return rc;
-        if (timed) {
-            GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used + 1], st));
-            ++e->ev_used;
+        if (e->use_graph && !e->timing && !e->slab) {
+            gof_engine::StepGraph& sg = e->graphs[e->parity];
+            if (!sg.exec || sg.timestep != timestep || sg.wrap_mode != wrap_mode || sg.split != g_force_split ||
+                sg.packed != engine_packed(e) || sg.generation != e->generation)
+                if (int rc = engine_capture_step(e, timestep, wrap_mode)) return rc;
+            GOF_CUDA(cudaGraphLaunch(sg.exec, st));
+            g_launches.fetch_add((uint64_t)sg.launches, std::memory_order_relaxed);
+            e->binned = true;
+            e->binned_packed = sg.packed;
+        } else {
+            if (int rc = engine_enqueue_step(e, timestep, wrap_mode, st, timed)) return rc;
         }
         e->parity ^= 1;
     }

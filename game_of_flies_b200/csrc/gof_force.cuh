@@ -502,16 +502,30 @@ __device__ __forceinline__ void run_pairs_zquirk(Home& h, RowAddr tabrow_s, cons
         quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j, ldg4(a.posw + j));
 }
 
+// Split kernel: run q's partial sum of this warp's home particle, [run][component][home lane].
+constexpr int kSplitHomes = 32;
+constexpr int kSplitRuns = 18;  // 9 stencil rows x (un-shifted x cells, cell across the x boundary)
+__device__ __forceinline__ void store_partial(float* __restrict__ part, int q, const Home& h)
+{
+    part[(q * 3 + 0) * kSplitHomes] = h.ax;
+    part[(q * 3 + 1) * kSplitHomes] = h.ay;
+    part[(q * 3 + 2) * kSplitHomes] = h.az;
+}
+
 // The whole stencil of ONE home particle on the literal path, out of line: the fast path of the
 // kernel keeps its own register allocation, and an edge-layer lane pays one call.
 // Same run structure and partial sums as the fast path (per row: the un-shifted x cells in
 // ascending order, then the cell across the x boundary), so that a particle's result does not
 // depend on which path its warp-mates take.
-template <bool BOIDS>
+//
+// SPLIT > 1 (small systems, see k_force): only the stencil rows of this warp's share are walked and
+// every run's partial sum goes to `part` (shared memory) instead of being folded here.
+template <bool BOIDS, int SPLIT>
 __device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type, unsigned kinds,
                                           RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
                                           float* __restrict__ boid_acc, const ForceArgs& a,
-                                          const Geometry& g, int cx, int cy, int lz, int gz, bool valid)
+                                          const Geometry& g, int cx, int cy, int lz, int gz, bool valid,
+                                          int share, int rows_per_share, float* __restrict__ part)
 {
     Home h;
     h.x = hx; h.y = hy; h.z = hz;
@@ -520,6 +534,7 @@ __device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type
     h.type = type;
     h.kinds = kinds;
     const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
+    int row = 0;
     for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
         int nl = lz + dzi;
         const int ngz = gz + dzi;
@@ -527,7 +542,8 @@ __device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type
             if (ngz < 0) nl += g.nbz;
             else if (ngz >= g.nbz) nl -= g.nbz;
         }
-        for (int dyi = -1; dyi <= 1; ++dyi) {
+        for (int dyi = -1; dyi <= 1; ++dyi, ++row) {
+            if (SPLIT > 1 && row / rows_per_share != share) continue;
             int ny = cy + dyi, sy = 0;
             if (ny < 0) { ny += g.nby; sy = 1; }
             else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
@@ -555,6 +571,7 @@ __device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type
                 const int e = valid ? a.pstart[rb + hi] + a.count[rb + hi] : s;
                 run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, direct);
             }
+            if (SPLIT > 1) store_partial(part, 2 * row, h);
             h.ax += ax0; h.ay += ay0; h.az += az0;
             ax0 = h.ax; ay0 = h.ay; az0 = h.az;
             h.ax = h.ay = h.az = 0.0f;
@@ -566,19 +583,33 @@ __device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type
                 const int e = valid ? s + a.count[rb + wc] : s;
                 run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, cx == 0 ? 1 : -1, sy, direct);
             }
+            if (SPLIT > 1) store_partial(part, 2 * row + 1, h);
             h.ax += ax0; h.ay += ay0; h.az += az0;
         }
     }
     return make_float3(h.ax, h.ay, h.az);
 }
 
-template <bool BOIDS, int MODE>
+//
+// SPLIT > 1 is the small-system variant (Clusters kind only).  With one thread per particle a
+// system of a few thousand particles cannot fill 148 SMs, and a step costs the latency of one
+// thread walking ~1000 candidates.  Here a block is 32 home particles x SPLIT warps; warp w walks
+// only the stencil rows of share w (one row, or one dz plane) and leaves every run's partial sum
+// in shared memory; warp 0 then folds the 18 partials in the order the one-thread kernel adds
+// them, so the result is bit-identical to SPLIT == 1 whatever the split.
 #ifndef GOF_FORCE_MINBLOCKS
 #define GOF_FORCE_MINBLOCKS 5
 #endif
-__global__ void __launch_bounds__(kForceThreads, GOF_FORCE_MINBLOCKS)
+template <bool BOIDS, int MODE, int SPLIT>
+__global__ void __launch_bounds__(SPLIT == 1 ? kForceThreads : kSplitHomes * SPLIT,
+                                  SPLIT == 1 ? GOF_FORCE_MINBLOCKS : (SPLIT == 3 ? 6 : 2))
 k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
 {
+    static_assert(SPLIT == 1 || !BOIDS, "the split variant covers Clusters-kind systems only");
+    constexpr int kHomes = SPLIT == 1 ? kForceThreads : kSplitHomes;  // home particles per block
+    const int hl = SPLIT == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31u);
+    const int share = SPLIT == 1 ? 0 : (int)(threadIdx.x >> 5);
+    const int rows_per_share = SPLIT == 1 ? 9 : (g.is3d ? 9 : 3) / SPLIT;
     extern __shared__ float4 smem_raw[];
     PairParam* tab = reinterpret_cast<PairParam*>(smem_raw);
     const int T = a.T;
@@ -586,6 +617,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     float4* tabA = reinterpret_cast<float4*>(tab + T * T);
     float2* tabB = reinterpret_cast<float2*>(tabA + T * TA);
     float* boid_acc = reinterpret_cast<float*>(tabB + T * TA + (T * TA & 1)) + threadIdx.x;
+    float* part = reinterpret_cast<float*>(tabB + T * TA + (T * TA & 1)) + hl;  // SPLIT > 1 only
     for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
         const PairParam pp = a.table[q];
         tab[q] = pp;
@@ -611,11 +643,11 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     // the kernel's tail.  (Single periodic box only: a slab launches its boundary layers apart.)
     int first_block = 0;
     if (g.is3d && g.index_wrap_z && a.wrap_mode == kWrapReference && a.home_count2 == 0 && !a.interior_words)
-        first_block = (a.pstart[(g.nlz - 1) * g.nbx * g.nby] - home_begin) / (int)blockDim.x;
+        first_block = (a.pstart[(g.nlz - 1) * g.nbx * g.nby] - home_begin) / kHomes;
     int blk = (int)blockIdx.x + first_block;
     if (blk >= (int)gridDim.x) blk -= (int)gridDim.x;
-    const int local = blk * blockDim.x + threadIdx.x;
-    if (a.interior_words && local - (int)threadIdx.x >= home_count) return;  // whole block past the range
+    const int local = blk * kHomes + hl;
+    if (a.interior_words && local - hl >= home_count) return;  // whole block past the range
     const bool valid = local < home_count + a.home_count2;
     int k = home_begin + (local < home_count ? local : home_count - 1);
     if (local >= home_count && a.home_count2 > 0)
@@ -649,6 +681,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
 
     const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
     if (!quirk) {
+        int row = 0;
         for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
             int nl = lz + dzi, sz = 0;
             if (g.is3d) {
@@ -656,7 +689,8 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 if (ngz < 0) { sz = 1; if (g.index_wrap_z) nl += g.nbz; }
                 else if (ngz >= g.nbz) { sz = -1; if (g.index_wrap_z) nl -= g.nbz; }
             }
-            for (int dyi = -1; dyi <= 1; ++dyi) {
+            for (int dyi = -1; dyi <= 1; ++dyi, ++row) {
+                if (SPLIT > 1 && row / rows_per_share != share) continue;
                 int ny = cy + dyi, sy = 0;
                 if (ny < 0) { ny += g.nby; sy = 1; }
                 else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
@@ -668,6 +702,10 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 int e = a.pstart[rb + hi] + a.count[rb + hi];
                 if (!valid) e = s;
                 run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, 0, sy, sz, s, e);
+                if (SPLIT > 1) {
+                    store_partial(part, 2 * row, h);
+                    h.ax = h.ay = h.az = 0.0f;
+                }
                 // the cell across the periodic x boundary (an empty run for interior home cells:
                 // every lane makes the same calls, so the warp votes inside stay convergent)
                 const bool xedge = cx == 0 || cx == g.nbx - 1;
@@ -675,12 +713,29 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 s = a.pstart[rb + wc];
                 e = (valid && xedge) ? s + a.count[rb + wc] : s;
                 run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e);
+                if (SPLIT > 1) {
+                    store_partial(part, 2 * row + 1, h);
+                    h.ax = h.ay = h.az = 0.0f;
+                }
             }
         }
     } else {
-        const float3 f = quirk_home<BOIDS>(h.x, h.y, h.z, h.type, h.kinds, tabrow_s, tabrow, boid_acc, a, g, cx, cy,
-                                           lz, gz, valid);
+        const float3 f = quirk_home<BOIDS, SPLIT>(h.x, h.y, h.z, h.type, h.kinds, tabrow_s, tabrow, boid_acc, a, g,
+                                                  cx, cy, lz, gz, valid, share, rows_per_share, part);
         h.ax = f.x; h.ay = f.y; h.az = f.z;
+    }
+    if (SPLIT > 1) {
+        // fold the run partials exactly as the one-thread kernel does: total = partial + total
+        __syncthreads();
+        if (share != 0) return;
+        const int runs = g.is3d ? kSplitRuns : kSplitRuns / 3;
+        float tx = 0.0f, ty = 0.0f, tz = 0.0f;
+        for (int q = 0; q < runs; ++q) {
+            tx = part[(q * 3 + 0) * kSplitHomes] + tx;
+            ty = part[(q * 3 + 1) * kSplitHomes] + ty;
+            tz = part[(q * 3 + 2) * kSplitHomes] + tz;
+        }
+        h.ax = tx; h.ay = ty; h.az = tz;
     }
 
     // ---- cohesion and alignment from the per-type means (acceleration_updater.py:422-458) ----

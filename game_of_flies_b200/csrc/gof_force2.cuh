@@ -340,9 +340,9 @@ k_force2(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a
             RowAddr tabrow_s;
             tabrow_s.a = (unsigned)__cvta_generic_to_shared(tabA + type * TA);
             tabrow_s.b = (unsigned)__cvta_generic_to_shared(tabB + type * TA);
-            const float3 f = quirk_home<false>(which ? h.x.y : h.x.x, which ? h.y.y : h.y.x, which ? h.z.y : h.z.x,
-                                               type, 0u, tabrow_s, tab + type * T, nullptr, a, g, cx, cy, lz, gz,
-                                               valid);
+            const float3 f = quirk_home<false, 1>(which ? h.x.y : h.x.x, which ? h.y.y : h.y.x, which ? h.z.y : h.z.x,
+                                                  type, 0u, tabrow_s, tab + type * T, nullptr, a, g, cx, cy, lz, gz,
+                                                  valid, 0, 9, nullptr);
             if (which) { h.ax.y = f.x; h.ay.y = f.y; h.az.y = f.z; }
             else       { h.ax.x = f.x; h.ay.x = f.y; h.az.x = f.z; }
         }

@@ -155,6 +155,10 @@ class ParticleEngine:
         _lib.check(self.lib.gof_engine_last_timestep(self._handle, C.byref(out), self._stream()))
         return float(out.value)
 
+    def set_graph(self, enable: bool):
+        """One CUDA graph launch per step (default) or individual kernel launches; same results."""
+        _lib.check(self.lib.gof_engine_set_graph(self._handle, 1 if enable else 0))
+
     def timing(self, enable: bool):
         """Bracket every force-kernel launch with CUDA events (bench.py roofline)."""
         _lib.check(self.lib.gof_engine_timing(self._handle, 1 if enable else 0))

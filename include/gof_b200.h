@@ -198,6 +198,15 @@ int gof_engine_read_bins(gof_engine *e, int32_t *particle_bins_any, int32_t *bin
 #define GOF_KERNEL_PACKED 1
 int gof_engine_set_kernel(gof_engine *e, int kernel);
 
+/* gof_engine_step launches every step as one CUDA graph (captured on first use, per timestep
+ * value and wrap mode); enable = 0 goes back to individual kernel launches.  Same results. */
+int gof_engine_set_graph(gof_engine *e, int enable);
+
+/* Small-system tuning knob of the scalar kernel (process-wide).  For Clusters-kind systems the
+ * 9 (3 in 2D) stencil rows of a home particle can be walked by 3 or 9 warps instead of one
+ * thread; -1 (default) picks by system size.  Results are bit-identical whatever the value. */
+int gof_set_force_split(int split);
+
 /* Per-kernel timing for bench.py's roofline: when enabled, gof_engine_step brackets every
  * force-kernel launch with CUDA events on `stream` (up to 4096 launches per enable).
  * gof_engine_force_time synchronises on the recorded events and returns the summed

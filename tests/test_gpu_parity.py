@@ -226,6 +226,66 @@ def test_engine_step_random_states(gof, kinds, counts, limits, speed, ts):
     check_engine_step(gof, st, ts, wrap_mode=orc.WRAP_MINIMAGE, packed=True)
 
 
+@pytest.mark.parametrize("wrap_mode", [orc.WRAP_REFERENCE, orc.WRAP_MINIMAGE], ids=["refwrap", "minimage"])
+@pytest.mark.parametrize("counts,limits", [
+    ([900] * 3, (100, 100, 0)),          # 2D: rows split over 3 warps
+    ([1500] * 5, (60, 75, 45)),          # 3D, 3 z layers: most particles on the literal z-wrap path
+    ([4000] * 4, (130, 120, 140)),       # 3D, interior and edge layers
+])
+def test_split_force_kernel_is_bit_identical_to_the_one_thread_kernel(gof, counts, limits, wrap_mode):
+    """Small Clusters systems spread a home particle's stencil rows over 3 or 9 warps
+    (gof_set_force_split); the partial sums are folded in the one-thread kernel's order."""
+    st = random_state(counts, limits, seed=77, kinds="clusters", speed=2.0)
+    lib = gof.lib.load()
+    outs = {}
+    try:
+        for split in (1, 3, 9, -1):
+            gof.lib.check(lib.gof_set_force_split(split))
+            e = engine_from_state(gof, st, wrap_mode)
+            e.step(3)
+            outs[split] = e.download(pos=True, vel=True, acc=True)
+            e.close()
+            # the reference-layout entry point (accelerations scattered to particle order)
+            bins = run_setup_bins(gof, st["pos"], oracle_sim(st).grid)
+            outs[split]["scatter"], _, _ = run_accelerator(gof, st, bins, wrap_mode, with_boid_outputs=False)
+    finally:
+        gof.lib.check(lib.gof_set_force_split(-1))
+    assert lib.gof_set_force_split(5) != 0  # rejected
+    for split in (3, 9, -1):
+        for k in ("pos", "vel", "acc", "scatter"):
+            assert np.array_equal(outs[1][k], outs[split][k]), f"split {split}: {k} differs"
+
+
+@pytest.mark.parametrize("kinds,counts,limits", [
+    ("clusters", [700, 700, 600], (100, 100, 0)),
+    ("mixed", [900] * 4, (70, 70, 70)),
+])
+def test_graph_launched_steps_equal_kernel_launched_steps(gof, kinds, counts, limits):
+    """gof_engine_step replays one captured CUDA graph per step; switching timestep mode,
+    parameters or wrap mode must re-capture, and nothing may differ from plain launches."""
+    st = random_state(counts, limits, seed=31, kinds=kinds, speed=3.0)
+    outs = []
+    for graph in (True, False):
+        e = engine_from_state(gof, st)
+        e.set_graph(graph)
+        e.step(5)              # adaptive timestep
+        e.step(3, 0.02)        # fixed
+        e.step(1, 0.01)        # another value: baked into the graph, must be re-captured
+        e.step(4)
+        pm = st["parameter_matrix"].copy()
+        pm[3, 0, 1] *= 1.5
+        e.set_parameters(pm)
+        e.step(3)
+        e.wrap_mode = orc.WRAP_MINIMAGE
+        e.step(2)
+        outs.append(e.download(pos=True, vel=True, acc=True))
+        outs[-1]["dt"] = e.last_timestep()
+        e.close()
+    for k in ("pos", "vel", "acc"):
+        assert np.array_equal(outs[0][k], outs[1][k]), f"{k}: graph and plain launches differ"
+    assert outs[0]["dt"] == outs[1]["dt"]
+
+
 def test_engine_is_deterministic_and_keeps_every_particle(gof):
     st = random_state([30000] * 5, (220, 220, 220), seed=5, kinds="clusters", speed=1.0)
     outs = []
