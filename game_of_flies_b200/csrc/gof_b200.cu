@@ -185,7 +185,9 @@ static int make_geometry(const gof_grid* grid, int layer_base, int local_layers,
 // --------------------------------------------------------------------------------------
 struct HostSpecies {
     int T = 0;
-    bool has_boids = false;
+    bool has_boids = false;     // some pair is of the Boids kind
+    bool has_clusters = false;  // some pair is not
+    int kind() const { return !has_boids ? kKindClusters : (has_clusters ? kKindMixed : kKindBoids); }
     std::vector<PairParam> table;
     std::vector<unsigned> kind_rows;
     std::vector<double> sep_exact;
@@ -215,7 +217,7 @@ static int build_species(const double* pm, int T, HostSpecies* out)
 {
     if (!pm || T < 1 || T > GOF_MAX_TYPES) return fail(GOF_E_INVALID, "num_types must be in [1, 16]");
     out->T = T;
-    out->has_boids = false;
+    out->has_boids = out->has_clusters = false;
     out->table.assign((size_t)T * T, PairParam{});
     out->kind_rows.assign(T, 0u);
     out->sep_exact.assign((size_t)T * T, 0.0);
@@ -227,6 +229,7 @@ static int build_species(const double* pm, int T, HostSpecies* out)
             const double a0 = pm[0 * TT + q], a1 = pm[1 * TT + q], a2 = pm[2 * TT + q], a3 = pm[3 * TT + q];
             const double kind = pm[4 * TT + q];
             PairParam p{};
+            if (kind != 1.0) out->has_clusters = true;
             if (kind == 1.0) {
                 out->has_boids = true;
                 out->kind_rows[i] |= 1u << j;
@@ -273,26 +276,27 @@ static int upload_species(const HostSpecies& h, const DeviceSpecies& d, cudaStre
     return 0;
 }
 
-static size_t force_smem_bytes(int T, bool boids, int split)
+static size_t force_smem_bytes(int T, int kind, int split)
 {
     const size_t TA = (size_t)(T | 1);
     return (size_t)T * T * sizeof(PairParam) + (size_t)T * TA * (sizeof(float4) + sizeof(float2)) + 16 +
-           (boids ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0) +
+           (kind != kKindClusters ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0) +
+           (kind == kKindBoids ? (size_t)kQueueDepth * kForceThreads * sizeof(unsigned) : 0) +
            (split > 1 ? (size_t)kSplitRuns * 3 * kSplitHomes * sizeof(float) : 0);
 }
 
-template <bool BOIDS, int MODE, int SPLIT>
+template <int KIND, int MODE, int SPLIT>
 static int launch_force_t(const Geometry& g, const ForceArgs& a, cudaStream_t st)
 {
-    const size_t smem = force_smem_bytes(a.T, BOIDS, SPLIT);
+    const size_t smem = force_smem_bytes(a.T, KIND, SPLIT);
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
-        GOF_CUDA(cudaFuncSetAttribute(k_force<BOIDS, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GOF_CUDA(cudaFuncSetAttribute(k_force<KIND, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       100 * 1024));
         attr_set = true;
     }
     const int homes = SPLIT == 1 ? kForceThreads : kSplitHomes;
-    GOF_LAUNCH((k_force<BOIDS, MODE, SPLIT>), cdiv(a.home_count + a.home_count2, homes), homes * SPLIT, smem, st, g, a);
+    GOF_LAUNCH((k_force<KIND, MODE, SPLIT>), cdiv(a.home_count + a.home_count2, homes), homes * SPLIT, smem, st, g, a);
     return 0;
 }
 
@@ -321,22 +325,28 @@ extern "C" int gof_set_force_split(int split)
 }
 
 template <int MODE>
-static int launch_force_m(const Geometry& g, const ForceArgs& a, bool boids, cudaStream_t st)
+static int launch_force_m(const Geometry& g, const ForceArgs& a, int kind, cudaStream_t st)
 {
-    if (boids) return launch_force_t<true, MODE, 1>(g, a, st);
+    if (kind == kKindBoids) {
+        // queue entries hold a slot index in kQueueSlotBits bits (slots: owned + halo particles)
+        if (a.slot_limit > (1 << kQueueSlotBits))
+            return fail(GOF_E_INVALID, "at most 2^26 particle slots per engine while a species pair is Boids-kind");
+        return launch_force_t<kKindBoids, MODE, 1>(g, a, st);
+    }
+    if (kind == kKindMixed) return launch_force_t<kKindMixed, MODE, 1>(g, a, st);
     switch (pick_split(g, a.home_count + a.home_count2, false)) {
-        case 9: return launch_force_t<false, MODE, 9>(g, a, st);
-        case 3: return launch_force_t<false, MODE, 3>(g, a, st);
-        default: return launch_force_t<false, MODE, 1>(g, a, st);
+        case 9: return launch_force_t<kKindClusters, MODE, 9>(g, a, st);
+        case 3: return launch_force_t<kKindClusters, MODE, 3>(g, a, st);
+        default: return launch_force_t<kKindClusters, MODE, 1>(g, a, st);
     }
 }
 
 // a.home_count is the number of threads to launch (an upper bound when a.interior_words is set)
-static int launch_force(const Geometry& g, const ForceArgs& a, bool boids, int mode, cudaStream_t st)
+static int launch_force(const Geometry& g, const ForceArgs& a, int kind, int mode, cudaStream_t st)
 {
     if (a.home_count + a.home_count2 <= 0) return 0;
-    if (mode == kModeIntegrate) return launch_force_m<kModeIntegrate>(g, a, boids, st);
-    return launch_force_m<kModeScatter>(g, a, boids, st);
+    if (mode == kModeIntegrate) return launch_force_m<kModeIntegrate>(g, a, kind, st);
+    return launch_force_m<kModeScatter>(g, a, kind, st);
 }
 
 // exclusive scan of m ints (PAD2: of the counts rounded up to even); tile_sums needs
@@ -676,7 +686,8 @@ extern "C" int gof_accelerator(const float* d_pos_x, const float* d_pos_y, const
     a.boid_vel_y = d_boid_vel_y;
     a.boid_vel_z = d_boid_vel_z;
     a.n_total = n;
-    return launch_force(g, a, hs.has_boids, kModeScatter, st);
+    a.slot_limit = n;
+    return launch_force(g, a, hs.kind(), kModeScatter, st);
 }
 
 extern "C" int gof_step1(float* vx, float* vy, float* vz, const float* ax, const float* ay, const float* az,
@@ -1013,7 +1024,7 @@ static int engine_bin(gof_engine* e, bool kick, cudaStream_t st)
 static int engine_force(gof_engine* e, const ForceArgs& a, cudaStream_t st)
 {
     if (engine_packed(e)) return launch_force2(e->geom, a, e->n + e->geom.num_cells, st);
-    return launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st);
+    return launch_force(e->geom, a, e->species.kind(), kModeIntegrate, st);
 }
 
 static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
@@ -1038,6 +1049,7 @@ static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
     a->acc_out = e->acc;
     a->scalars = e->scalars;
     a->n_total = e->n;
+    a->slot_limit = e->slot_capacity;
 }
 
 // the launches of one core_step at the engine's current parity (which the caller flips)
@@ -1455,7 +1467,7 @@ static int slab_timed_force(gof_engine* e, const ForceArgs& a, cudaStream_t st)
         }
         GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used], st));
     }
-    if (int rc = launch_force(e->geom, a, e->species.has_boids, kModeIntegrate, st)) return rc;
+    if (int rc = launch_force(e->geom, a, e->species.kind(), kModeIntegrate, st)) return rc;
     if (timed) {
         GOF_CUDA(cudaEventRecord(e->ev[2 * e->ev_used + 1], st));
         ++e->ev_used;

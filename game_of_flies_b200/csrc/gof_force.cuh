@@ -22,6 +22,13 @@ namespace gof {
 constexpr int kForceThreads = 128;
 constexpr int kBoidSlots = 7;  // per partner type: count, sum of relative positions (3), sum of velocities (3)
 
+// which kinds of species pairs a launch has to handle (decides the code of the hot loop)
+enum ForceKind : int {
+    kKindClusters = 0,  // every pair is of the Clusters kind: branch-free masked evaluation
+    kKindMixed = 1,     // both kinds: test, interaction behind a branch
+    kKindBoids = 2,     // every pair is of the Boids kind: test + note, interactions deferred
+};
+
 enum ForceMode : int {
     kModeIntegrate = 0,  // engine: fused step2 + boundary condition + max |v|^2, outputs in cell order
     kModeScatter = 1,    // reference-layout API: accelerations (and boid sums) scattered to particle order
@@ -58,6 +65,7 @@ struct ForceArgs {
     int* boid_counts; float* boid_acc_x; float* boid_acc_y; float* boid_acc_z;
     float* boid_vel_x; float* boid_vel_y; float* boid_vel_z;
     int n_total;
+    int slot_limit;           // upper bound of the indices into posw / veli (Boids-kind queue entries)
 };
 
 // Per-thread state of the particle being updated.
@@ -104,6 +112,35 @@ __device__ __forceinline__ float fast_rsqrt(float v)
 //   (dx, dy, dz) = home - neighbour (after the periodic shift), d2 = |d|^2
 //   (rx, ry, rz) = neighbour - home as the reference accumulates it for cohesion
 //   exact_d2()   = the float64 squared distance, evaluated only on the edge of r_sep
+// boids(): separation inside r_sep, and the per-type sums for cohesion / alignment
+template <typename ExactD2>
+__device__ __forceinline__ void interact_boids(Home& h, const float4 qa, float* __restrict__ boid_acc,
+                                               const ForceArgs& a, int T, int j, int tj, float dx, float dy,
+                                               float dz, float rx, float ry, float rz, float inv, float dist,
+                                               ExactD2 exact_d2)
+{
+    bool sep = dist < qa.x;
+    if (fabsf(dist - qa.x) < 4e-6f * qa.x) {
+        // on the edge of the separation radius the decision is taken in float64
+        sep = sqrt(exact_d2()) < a.sep_exact[h.type * T + tj];
+    }
+    if (sep) {
+        const float s = qa.y * inv;
+        h.ax = fmaf(s, dx, h.ax);
+        h.ay = fmaf(s, dy, h.ay);
+        h.az = fmaf(s, dz, h.az);
+    }
+    const float4 vj = ldg4(a.veli + j);
+    float* slot = boid_acc + tj * kBoidSlots * kForceThreads;
+    slot[0 * kForceThreads] += 1.0f;
+    slot[1 * kForceThreads] += rx;
+    slot[2 * kForceThreads] += ry;
+    slot[3 * kForceThreads] += rz;
+    slot[4 * kForceThreads] += vj.x;
+    slot[5 * kForceThreads] += vj.y;
+    slot[6 * kForceThreads] += vj.z;
+}
+
 template <bool BOIDS, typename ExactD2>
 __device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ tabrow,
                                          float* __restrict__ boid_acc, const ForceArgs& a,
@@ -123,27 +160,7 @@ __device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ 
         h.ay = fmaf(-s, dy, h.ay);
         h.az = fmaf(-s, dz, h.az);
     } else {
-        // boids(): separation inside r_sep, and the per-type sums for cohesion / alignment
-        bool sep = dist < qa.x;
-        if (fabsf(dist - qa.x) < 4e-6f * qa.x) {
-            // on the edge of the separation radius the decision is taken in float64
-            sep = sqrt(exact_d2()) < a.sep_exact[h.type * T + tj];
-        }
-        if (sep) {
-            const float s = qa.y * inv;
-            h.ax = fmaf(s, dx, h.ax);
-            h.ay = fmaf(s, dy, h.ay);
-            h.az = fmaf(s, dz, h.az);
-        }
-        const float4 vj = ldg4(a.veli + j);
-        float* slot = boid_acc + tj * kBoidSlots * kForceThreads;
-        slot[0 * kForceThreads] += 1.0f;
-        slot[1 * kForceThreads] += rx;
-        slot[2 * kForceThreads] += ry;
-        slot[3 * kForceThreads] += rz;
-        slot[4 * kForceThreads] += vj.x;
-        slot[5 * kForceThreads] += vj.y;
-        slot[6 * kForceThreads] += vj.z;
+        interact_boids(h, qa, boid_acc, a, T, j, tj, dx, dy, dz, rx, ry, rz, inv, dist, exact_d2);
     }
 }
 
@@ -228,8 +245,11 @@ __device__ __noinline__ float3 repair_pair_clusters(const Geometry& g, float xi,
     return make_float3(-s * dx, -s * dy, -s * dz);
 }
 
-// Branch-free Clusters pair (see `pair` below).  Adds the force iff d2 < r2_lo and
-// returns d2 so that the caller can spot the rare pairs that need the cold path.
+// Branch-free Clusters pair.  With ~830 candidates and ~130 neighbours per particle at least one
+// lane of a warp accepts almost every candidate, so a branch around the force evaluation never
+// skips it; it only adds divergence bookkeeping and serialises the loop.  The evaluation is
+// therefore done for every candidate and masked: adds the force iff d2 < r2_lo and returns d2 so
+// that the caller can spot the rare pairs that need the cold path.
 template <bool LOWFIX>
 __device__ __forceinline__ float pair_clusters(Home& h, RowAddr tabrow_s, const Geometry& g,
                                                const Image& im, const float4 pj)
@@ -266,56 +286,152 @@ __device__ __forceinline__ void repair(Home& h, const PairParam* __restrict__ ta
     h.ax += f.x; h.ay += f.y; h.az += f.z;
 }
 
-// Distance test + interaction of one neighbour.
-//  BOIDS = false: every species pair is of the Clusters kind.  With ~830 candidates and
-//  ~130 neighbours per particle at least one lane of a warp accepts almost every candidate,
-//  so a branch around the force evaluation never skips it; it only adds divergence
-//  bookkeeping and serialises the loop.  The evaluation is therefore done for every
-//  candidate and masked: 23 issue slots per candidate instead of ~33, no divergence.
-//  BOIDS = true: the per-type sums make the accepted path long; it stays behind a branch.
-template <bool BOIDS, bool LOWFIX>
-__device__ __forceinline__ void pair(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
-                                     float* __restrict__ boid_acc, const ForceArgs& a,
-                                     const Geometry& g, const Image& im, int j, const float4 pj)
+// ---- systems with Boids-kind pairs: deferred interactions ----------------------------------
+// A Boids-kind pair that is in range costs ~40 instructions (its velocity load and seven
+// shared-memory sums), and behind a branch in the candidate loop it runs with the few lanes that
+// accepted this neighbour (measured: 15 of 32 lanes active on average).  Instead the candidate
+// loop only NOTES a pair that is in range -- the neighbour's index goes to a per-lane queue in
+// shared memory, one predicated store -- and the queue is drained with every lane working on
+// ITS OWN entries.  A lane's entries are in run order, so its sums are formed in the same order
+// whenever the drains happen.
+#ifndef GOF_QUEUE_DEPTH
+#define GOF_QUEUE_DEPTH 32
+#endif
+constexpr int kQueueDepth = GOF_QUEUE_DEPTH;  // entries per lane; drained before a lane could overflow
+
+struct BoidQueue {
+    unsigned base;   // shared-memory address of this lane's entry 0 (entries kForceThreads * 4 bytes apart)
+    int count;
+    float fx, fy, fz;  // force of the drained pairs so far, summed in queue order
+};
+
+// An entry is the neighbour's slot and the periodic image of the run it was met in:
+// slot | packed shifts << 26 (at most 2^26 slots per engine while a species pair is Boids-kind).
+constexpr int kQueueSlotBits = 26;
+
+__device__ __forceinline__ void queue_push(BoidQueue& q, unsigned entry, bool hit)
+{
+    if (hit) asm volatile("st.shared.b32 [%0], %1;" ::"r"(q.base + (unsigned)q.count * (kForceThreads * 4u)), "r"(entry));
+    q.count += hit ? 1 : 0;
+}
+
+// Systems with Boids-kind pairs: the hot loop is nothing but the test and the note.
+template <bool LOWFIX>
+__device__ __forceinline__ void pair_note(const Geometry& g, const Image& im, const float4 pj, unsigned entry,
+                                          BoidQueue& q)
 {
     float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
     if (LOWFIX) { dx += im.lx; dy += im.ly; dz += im.lz; }
     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const bool in = d2 < g.r2_hi && d2 > 1e-10f;
-    if (!BOIDS) {
-        // (tail of a run; the unrolled body of run_pairs calls pair_clusters directly)
-        if (needs_repair(g, pair_clusters<LOWFIX>(h, tabrow_s, g, im, pj))) repair(h, tabrow, g, im, pj);
-    } else if (in) {
+    queue_push(q, entry, d2 < g.r2_hi && d2 > 1e-10f);
+}
+
+// Out of line (one copy: the hot loops stay small).  The entries of a lane are handled one after
+// the other and add to ONE force accumulator in queue order, so the sum does not depend on where
+// the drains fall (a warp vote triggers them: warp-mates must not matter).  The queue outlives
+// the runs -- per run the lanes of a warp collect very different numbers of pairs (a particle in
+// the upper corner of its cell meets its neighbours in the upper rows), over the whole stencil
+// about the same -- so every entry rebuilds its periodic image from the packed shifts.  The `lo`
+// parts are zero for images that were not shifted upwards: adding them changes nothing.
+__device__ __noinline__ float3 queue_drain(float3 f, unsigned qbase, int count, float hx, float hy, float hz,
+                                           int type, unsigned kinds,
+                                           const PairParam* __restrict__ tabrow, float* __restrict__ boid_acc,
+                                           const ForceArgs& a, const Geometry& g)
+{
+    Home h;
+    h.x = hx; h.y = hy; h.z = hz;
+    h.vx = h.vy = h.vz = 0.0f;  // (not used by the pair interactions)
+    h.ax = f.x; h.ay = f.y; h.az = f.z;
+    h.type = type;
+    h.kinds = kinds;
+    for (int k = 0; k < count; ++k) {
+        unsigned entry;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(entry) : "r"(qbase + (unsigned)k * (kForceThreads * 4u)));
+        const int j = (int)(entry & ((1u << kQueueSlotBits) - 1u));
+        const int shifts = (int)(entry >> kQueueSlotBits);
+        const float4 pj = ldg4(a.posw + j);
+        float dx = hx - pj.x, dy = hy - pj.y, dz = hz - pj.z;
+        if (shifts != pack_shifts(0, 0, 0)) {  // met across a periodic boundary (home cells on the box faces)
+            const Image im = make_image(h, g, (shifts & 3) - 1, ((shifts >> 2) & 3) - 1, ((shifts >> 4) & 3) - 1);
+            dx = (im.x - pj.x) + im.lx; dy = (im.y - pj.y) + im.ly; dz = (im.z - pj.z) + im.lz;
+        }
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        bool ok = true;
+        if (d2 > g.r2_lo) {
+            const double e = exact_dist2(g, hx, hy, hz, pj.x, pj.y, pj.z, shifts);
+            ok = (1e-10 < e) && (e < g.r2d);
+        }
+        if (ok)
+            interact<true>(h, tabrow, boid_acc, a, a.T, j, __float_as_int(pj.w), dx, dy, dz, -dx, -dy, -dz, d2,
+                           [&]() { return exact_dist2(g, hx, hy, hz, pj.x, pj.y, pj.z, shifts); });
+    }
+    return make_float3(h.ax, h.ay, h.az);
+}
+
+__device__ __forceinline__ void drain(BoidQueue& q, const Home& h, const PairParam* __restrict__ tabrow,
+                                      float* __restrict__ boid_acc, const ForceArgs& a, const Geometry& g)
+{
+    const float3 f = queue_drain(make_float3(q.fx, q.fy, q.fz), q.base, q.count, h.x, h.y, h.z,
+                                 h.type, h.kinds, tabrow, boid_acc, a, g);
+    q.fx = f.x; q.fy = f.y; q.fz = f.z;
+    q.count = 0;
+}
+
+// Mixed systems (both kinds of pairs): distance test, then the interaction behind a branch.
+// (Queueing was measured here too: with ~130 pairs in range per particle the lanes of a warp fill
+// their queues at very different times -- a particle low in its cell meets its neighbours in the
+// first rows of the stencil walk -- and the drains ran 13 lanes wide: 3.0 ms against 2.6 ms.)
+template <bool LOWFIX>
+__device__ __forceinline__ void pair_branchy(Home& h, const PairParam* __restrict__ tabrow,
+                                             float* __restrict__ boid_acc, const ForceArgs& a,
+                                             const Geometry& g, const Image& im, int j, const float4 pj)
+{
+    float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
+    if (LOWFIX) { dx += im.lx; dy += im.ly; dz += im.lz; }
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (d2 < g.r2_hi && d2 > 1e-10f) {
         bool ok = true;
         if (d2 > g.r2_lo) {
             const double e = exact_dist2(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts);
             ok = (1e-10 < e) && (e < g.r2d);
         }
         if (ok)
-            interact<BOIDS>(h, tabrow, boid_acc, a, a.T, j, __float_as_int(pj.w), dx, dy, dz, -dx,
-                            -dy, -dz, d2,
-                            [&]() { return exact_dist2(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts); });
+            interact<true>(h, tabrow, boid_acc, a, a.T, j, __float_as_int(pj.w), dx, dy, dz, -dx, -dy, -dz, d2,
+                           [&]() { return exact_dist2(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts); });
     }
 }
 
 // A contiguous run [s, e) of neighbour particles seen through one periodic image.
 // Four independent 16-byte loads are issued before the four tests that consume them, so
 // the L1 latency of a neighbour is hidden behind the arithmetic of the previous ones.
-template <bool BOIDS, bool LOWFIX>
+template <int KIND, bool LOWFIX>
 __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
                                           const PairParam* __restrict__ tabrow,
                                           float* __restrict__ boid_acc, const ForceArgs& a,
-                                          const Geometry& g, const Image& im, int s, int e)
+                                          const Geometry& g, const Image& im, int s, int e, BoidQueue& q)
 {
     // the run sums into its own accumulator (shorter partial sums: less fp32 rounding)
     const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
     h.ax = h.ay = h.az = 0.0f;
+    const unsigned tag = (unsigned)im.shifts << kQueueSlotBits;
     int j = s;
     for (; j + 4 <= e; j += 4) {
         // four independent 16-byte loads issued ahead of the arithmetic that consumes them
         const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
                      p3 = ldg4(a.posw + j + 3);
-        if (!BOIDS) {
+        if (KIND == kKindBoids) {
+            pair_note<LOWFIX>(g, im, p0, tag | (unsigned)j, q);
+            pair_note<LOWFIX>(g, im, p1, tag | (unsigned)(j + 1), q);
+            pair_note<LOWFIX>(g, im, p2, tag | (unsigned)(j + 2), q);
+            pair_note<LOWFIX>(g, im, p3, tag | (unsigned)(j + 3), q);
+            // lanes drain together, each its own entries
+            if (__any_sync(__activemask(), q.count > kQueueDepth - 4)) drain(q, h, tabrow, boid_acc, a, g);
+        } else if (KIND == kKindMixed) {
+            pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j, p0);
+            pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j + 1, p1);
+            pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j + 2, p2);
+            pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j + 3, p3);
+        } else {
             // four independent, branch-free evaluations the scheduler can interleave; the rare
             // pairs in the guard band (~1 in 1e5) or below 1e-10 (the self pair) are repaired
             // after the group, found with one vote over the four squared distances
@@ -332,25 +448,29 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
                 if (needs_repair(g, d2)) repair(h, tabrow, g, im, p2);
                 if (needs_repair(g, d3)) repair(h, tabrow, g, im, p3);
             }
-        } else {
-            pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j, p0);
-            pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 1, p1);
-            pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 2, p2);
-            pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j + 3, p3);
         }
     }
-    for (; j < e; ++j) pair<BOIDS, LOWFIX>(h, tabrow_s, tabrow, boid_acc, a, g, im, j, ldg4(a.posw + j));
+    for (; j < e; ++j) {  // at most three
+        const float4 pj = ldg4(a.posw + j);
+        if (KIND == kKindBoids) pair_note<LOWFIX>(g, im, pj, tag | (unsigned)j, q);
+        else if (KIND == kKindMixed) pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j, pj);
+        else if (needs_repair(g, pair_clusters<LOWFIX>(h, tabrow_s, g, im, pj))) repair(h, tabrow, g, im, pj);
+    }
+    if (KIND == kKindBoids) {
+        // (the tail added at most three entries: room for the next group of four is kept here)
+        if (__any_sync(__activemask(), q.count > kQueueDepth - 4)) drain(q, h, tabrow, boid_acc, a, g);
+    }
     h.ax += ax0; h.ay += ay0; h.az += az0;
 }
 
 // Choice of the LOWFIX variant for the lanes that are converged here (every lane of a code
 // path walks the same sequence of runs, possibly empty).  The variant does not change a
 // lane's result when its own `lo` parts are zero, so the vote only saves instructions.
-template <bool BOIDS>
+template <int KIND>
 __device__ __forceinline__ void run_image(Home& h, RowAddr tabrow_s,
                                           const PairParam* __restrict__ tabrow,
                                           float* __restrict__ boid_acc, const ForceArgs& a,
-                                          const Geometry& g, int sx, int sy, int sz, int s, int e)
+                                          const Geometry& g, int sx, int sy, int sz, int s, int e, BoidQueue& q)
 {
     const Image im = make_image(h, g, sx, sy, sz);
 #ifdef GOF_LOWFIX_ALWAYS
@@ -358,9 +478,9 @@ __device__ __forceinline__ void run_image(Home& h, RowAddr tabrow_s,
 #else
     if (__any_sync(__activemask(), im.up && e > s))
 #endif
-        run_pairs<BOIDS, true>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
+        run_pairs<KIND, true>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e, q);
     else
-        run_pairs<BOIDS, false>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e);
+        run_pairs<KIND, false>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e, q);
 }
 
 // The reference's z wrap (acceleration_updater.py:325-328) tests pos_y[i] where it
@@ -600,11 +720,12 @@ __device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type
 #ifndef GOF_FORCE_MINBLOCKS
 #define GOF_FORCE_MINBLOCKS 5
 #endif
-template <bool BOIDS, int MODE, int SPLIT>
+template <int KIND, int MODE, int SPLIT>
 __global__ void __launch_bounds__(SPLIT == 1 ? kForceThreads : kSplitHomes * SPLIT,
                                   SPLIT == 1 ? GOF_FORCE_MINBLOCKS : (SPLIT == 3 ? 6 : 2))
 k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
 {
+    constexpr bool BOIDS = KIND != kKindClusters;
     static_assert(SPLIT == 1 || !BOIDS, "the split variant covers Clusters-kind systems only");
     constexpr int kHomes = SPLIT == 1 ? kForceThreads : kSplitHomes;  // home particles per block
     const int hl = SPLIT == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31u);
@@ -625,8 +746,14 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
         tabA[r * TA + c] = pp.a;
         tabB[r * TA + c] = make_float2(pp.b.x, pp.b.y);
     }
+    BoidQueue queue;
+    queue.base = 0u;
+    queue.count = 0;
+    queue.fx = queue.fy = queue.fz = 0.0f;
     if (BOIDS) {
         for (int q = 0; q < T * kBoidSlots; ++q) boid_acc[q * kForceThreads] = 0.0f;
+        // the queue sits behind the per-type sums; entry k of this lane at base + k * 512
+        queue.base = (unsigned)__cvta_generic_to_shared(boid_acc + T * kBoidSlots * kForceThreads);
     }
     __syncthreads();
 
@@ -701,7 +828,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 int s = a.pstart[rb + lo];
                 int e = a.pstart[rb + hi] + a.count[rb + hi];
                 if (!valid) e = s;
-                run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, 0, sy, sz, s, e);
+                run_image<KIND>(h, tabrow_s, tabrow, boid_acc, a, g, 0, sy, sz, s, e, queue);
                 if (SPLIT > 1) {
                     store_partial(part, 2 * row, h);
                     h.ax = h.ay = h.az = 0.0f;
@@ -712,12 +839,16 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 const int wc = cx == 0 ? g.nbx - 1 : 0;
                 s = a.pstart[rb + wc];
                 e = (valid && xedge) ? s + a.count[rb + wc] : s;
-                run_image<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e);
+                run_image<KIND>(h, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e, queue);
                 if (SPLIT > 1) {
                     store_partial(part, 2 * row + 1, h);
                     h.ax = h.ay = h.az = 0.0f;
                 }
             }
+        }
+        if (KIND == kKindBoids) {  // whatever is still queued; all forces of this path come from the queue
+            drain(queue, h, tabrow, boid_acc, a, g);
+            h.ax = queue.fx; h.ay = queue.fy; h.az = queue.fz;
         }
     } else {
         const float3 f = quirk_home<BOIDS, SPLIT>(h.x, h.y, h.z, h.type, h.kinds, tabrow_s, tabrow, boid_acc, a, g,
