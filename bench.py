@@ -420,7 +420,9 @@ def main():
         force_avg_ms = force_ms / max(force_launches, 1)
         achieved = FORCE_BYTES_PER_PARTICLE * n / (force_avg_ms * 1e-3) / 1e9
         roofline = {
-            "bound": "hbm", "kernel": "gof::k_force<false, integrate> (neighbour force + integrator)",
+            "bound": "hbm",
+            "kernel": "gof::k_force<%s, integrate> (neighbour force + integrator)"
+                      % {"clusters": "Clusters", "boids": "Boids", "mixed": "Mixed"}[WORKLOADS[args.workload][0]],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_src,
             "traffic": recorded_traffic(args.workload, n),
