@@ -50,6 +50,7 @@ static int fail(int code, const std::string& msg)
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
+
 extern "C" int gof_abi_version(void) { return GOF_ABI_VERSION; }
 extern "C" const char* gof_last_error(void) { return g_last_error.c_str(); }
 extern "C" uint64_t gof_launch_count(void) { return g_launches.load(); }
@@ -176,6 +177,12 @@ static int make_geometry(const gof_grid* grid, int layer_base, int local_layers,
     const double band = 2.0 * std::sqrt(3.0) * g.rmaxd * (3.0 * ulp) + 32.0 * 1.1920929e-7 * g.r2d;
     g.r2_lo = next_down((float)(g.r2d - band));
     g.r2_hi = next_up((float)(g.r2d + band));
+    g.cull_r2 = g.r2_hi * 1.0001f;
+    {
+        float m = g.Lx > g.Ly ? g.Lx : g.Ly;
+        if (g.Lz > m) m = g.Lz;
+        g.cull_slack = 2e-6f * m;  // a few ulps of a coordinate: images are rounded sums
+    }
     *out = g;
     return 0;
 }
@@ -282,7 +289,8 @@ static size_t force_smem_bytes(int T, int kind, int split)
     return (size_t)T * T * sizeof(PairParam) + (size_t)T * TA * (sizeof(float4) + sizeof(float2)) + 16 +
            (kind != kKindClusters ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0) +
            (kind == kKindBoids ? (size_t)kQueueDepth * kForceThreads * sizeof(unsigned) : 0) +
-           (split > 1 ? (size_t)kSplitRuns * 3 * kSplitHomes * sizeof(float) : 0);
+           (split > 1 ? (size_t)kSplitRuns * 3 * kSplitHomes * sizeof(float) : 0) +
+           (kind == kKindClusters ? (size_t)(split > 1 ? split : kForceThreads / 32) * kListLen * sizeof(float4) : 0);
 }
 
 template <int KIND, int MODE, int SPLIT>
@@ -524,7 +532,13 @@ k_export_bins(const float4* __restrict__ veli_sorted, const int* __restrict__ ce
     if (r >= count[c]) return;  // padding slot
     const int id = __float_as_int(veli_sorted[k].w);
     if (particle_bins) particle_bins[id] = c;
-    if (particle_indices) particle_indices[start[c] + r] = id;
+    if (particle_indices) {
+        // the reference's order inside a bin is by particle id; the engine's is by x
+        int by_id = 0;
+        for (int t = pstart[c], e = pstart[c] + count[c]; t < e; ++t)
+            by_id += __float_as_int(veli_sorted[t].w) < id;
+        particle_indices[start[c] + by_id] = id;
+    }
 }
 
 // reference-layout inputs -> cell-sorted float4 scratch for gof_accelerator
@@ -605,7 +619,8 @@ extern "C" int gof_setup_bins(const float* d_pos_x, const float* d_pos_y, const 
     if (int rc = launch_scan<false>(d_counts, num_bins, tile_sums, d_starts, st)) return rc;
     if (n > 0) {
         GOF_LAUNCH(k_scatter_ids<true>, cdiv(n, kBinThreads), kBinThreads, 0, st, (const float4*)nullptr, n,
-                   (const int*)nullptr, d_particle_bins, d_bin_offsets, d_starts, slot_id);
+                   (const int*)nullptr, d_particle_bins, d_bin_offsets, d_starts, slot_id, (const float4*)nullptr,
+                   (unsigned*)nullptr);
         GOF_LAUNCH(k_rank_indices, cdiv(n, kBinThreads), kBinThreads, 0, st, n, d_particle_bins, d_starts,
                    d_counts, slot_id, d_bin_offsets, d_particle_indices);
     }
@@ -755,6 +770,7 @@ struct gof_engine {
     size_t arena_bytes = 0;
     float4 *posw[2] = {nullptr, nullptr}, *veli[2] = {nullptr, nullptr}, *acc = nullptr;
     int *cell_of = nullptr, *off = nullptr, *slot_id = nullptr, *cell_sorted = nullptr;
+    unsigned* slot_key = nullptr;  // sort key inside a cell (bits of x), parallel to slot_id
     int *count = nullptr, *start = nullptr, *pstart = nullptr, *tile_sums = nullptr;
     int slot_capacity = 0;                      // capacity + num_cells + 2 (even-padded segments)
     StepScalars* scalars = nullptr;
@@ -819,6 +835,7 @@ static size_t engine_layout(gof_engine* e, char* base)
     e->cell_of = (int*)take(cap * sizeof(int));
     e->off = (int*)take(cap * sizeof(int));
     e->slot_id = (int*)take(slots * sizeof(int));
+    e->slot_key = (unsigned*)take(slots * sizeof(unsigned));
     e->cell_sorted = (int*)take(slots * sizeof(int));
     e->count = (int*)take(cells * sizeof(int));
     e->start = (int*)take(cells * sizeof(int));
@@ -984,6 +1001,17 @@ extern "C" int gof_engine_upload(gof_engine* e, const float* px, const float* py
     return 0;
 }
 
+// The order inside a cell: by x (see k_rank_gather_kick), or by id when built with GOF_NO_XSORT.
+static unsigned* engine_keys(gof_engine* e)
+{
+#ifdef GOF_NO_XSORT
+    (void)e;
+    return nullptr;
+#else
+    return e->slot_key;
+#endif
+}
+
 // Which force kernel a step uses: the packed two-homes kernel needs every species pair to be
 // of the Clusters kind (its profile is evaluated branch-free for both homes at once).
 static bool engine_packed(const gof_engine* e)
@@ -1010,10 +1038,10 @@ static int engine_bin(gof_engine* e, bool kick, cudaStream_t st)
         if (int rc = launch_scan<true>(e->count, g.num_cells + 1, e->tile_sums, e->pstart, st)) return rc;
     const int* layout = packed ? e->pstart : e->start;
     GOF_LAUNCH(k_scatter_ids<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->veli[0], n, (const int*)nullptr,
-               e->cell_of, e->off, layout, e->slot_id);
+               e->cell_of, e->off, layout, e->slot_id, e->posw[0], engine_keys(e));
     GOF_LAUNCH(k_rank_gather_kick, cdiv(n, kBinThreads), kBinThreads, 0, st, n, (const int*)nullptr, e->cell_of,
                layout, e->count,
-               e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1], e->cell_sorted,
+               e->slot_id, engine_keys(e), g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1], e->cell_sorted,
                packed ? 1 : 0, e->scalars, kick ? 1 : 0);
     e->binned = true;
     e->binned_packed = packed;
@@ -1429,9 +1457,10 @@ extern "C" int gof_slab_phase_sort_async(gof_engine* e, float timestep, void* st
     GOF_LAUNCH(k_prepare_dt, 1, 1, 0, st, e->scalars, e->parity, timestep < 0 ? -1.0f : timestep);
     if (int rc = launch_scan<false>(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
     GOF_LAUNCH(k_scatter_ids<false>, cdiv(bound, kBinThreads), kBinThreads, 0, st, e->veli[0], bound,
-               (const int*)(words + 1), e->cell_of, e->off, e->start, e->slot_id);
+               (const int*)(words + 1), e->cell_of, e->off, e->start, e->slot_id, e->posw[0], engine_keys(e));
     GOF_LAUNCH(k_rank_gather_kick, cdiv(bound, kBinThreads), kBinThreads, 0, st, bound, (const int*)(words + 1),
-               e->cell_of, e->start, e->count, e->slot_id, g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1],
+               e->cell_of, e->start, e->count, e->slot_id, engine_keys(e), g.num_cells, e->posw[0], e->veli[0], e->acc,
+               e->posw[1],
                e->veli[1], e->cell_sorted, 0, e->scalars, 1);
     GOF_LAUNCH(k_slab_counts, 1, 1, 0, st, e->start, e->counters + 2, e->counters + 4, g.num_cells, g.nbx * g.nby,
                g.nlz - 2);

@@ -213,16 +213,21 @@ k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_pre
 }
 
 // Arrival-order scatter of the ids into the cell segments (`start` may be the padded table).
+// The engine also scatters the sort key of the order INSIDE a cell: the bit pattern of x (x >= 0,
+// so the patterns order like the values); see k_rank_gather_kick.
 template <bool SOA>
 __global__ void __launch_bounds__(kBinThreads)
 k_scatter_ids(const float4* __restrict__ veli, int n, const int* __restrict__ n_limit,
               const int* __restrict__ cell_of, const int* __restrict__ off,
-              const int* __restrict__ start, int* __restrict__ slot_id)
+              const int* __restrict__ start, int* __restrict__ slot_id,
+              const float4* __restrict__ posw, unsigned* __restrict__ slot_key)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_limit) n = min(n, *n_limit);
     if (i >= n) return;
-    slot_id[start[cell_of[i]] + off[i]] = SOA ? i : __float_as_int(veli[i].w);
+    const int dst = start[cell_of[i]] + off[i];
+    slot_id[dst] = SOA ? i : __float_as_int(veli[i].w);
+    if (slot_key) slot_key[dst] = __float_as_uint(fabsf(posw[i].x));
 }
 
 // Rank pass for the reference-layout API: final position of every particle in its
@@ -258,8 +263,13 @@ struct StepScalars {
 
 constexpr float kDummyPos = 1e18f;  // a padding slot sits here: (1e18)^2 * 3 still fits fp32, never in range
 
-// One thread per SOURCE particle (rest order): its rank among the ids of its cell is its
-// slot in the cell's segment.  `pstart` is the table the segments are laid out with: the
+// One thread per SOURCE particle (rest order): its rank in its cell is its slot in the cell's
+// segment.  The order inside a cell is by x, ties by id (`slot_key` given), or by id alone.  By x
+// because the force kernel walks the candidates of a whole warp at once and culls them against
+// the box of the warp's 32 home particles: 32 consecutive particles nearly always straddle two
+// cells, and sorted by x they still span only about one cell width.  The order is a function of
+// the positions and ids alone, so it is the same on every decomposition.  The reference's
+// id-ordered `particle_indices` is re-derived on export (k_export_bins).  `pstart` is the table the segments are laid out with: the
 // true starts, or the even-padded starts (`padded`), in which case the last particle of an odd
 // cell also writes the dummy that fills the segment (the packed two-homes-per-lane force kernel
 // needs the two particles of a lane to share a cell).
@@ -267,6 +277,7 @@ __global__ void __launch_bounds__(kBinThreads)
 k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict__ cell_of,
                    const int* __restrict__ pstart,
                    const int* __restrict__ count, const int* __restrict__ slot_id,
+                   const unsigned* __restrict__ slot_key,
                    int sentinel_cell, const float4* __restrict__ posw_in,
                    const float4* __restrict__ veli_in, const float4* __restrict__ acc_in,
                    float4* __restrict__ posw_out, float4* __restrict__ veli_out,
@@ -281,8 +292,17 @@ k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict
     float4 v = veli_in[i];
     const int id = __float_as_int(v.w);
     const int b = pstart[c], cnt = count[c], e = b + cnt;
+    const float4 p = posw_in[i];
     int rank = 0;
-    for (int t = b; t < e; ++t) rank += (slot_id[t] < id);
+    if (slot_key) {
+        const unsigned key = __float_as_uint(fabsf(p.x));
+        for (int t = b; t < e; ++t) {
+            const unsigned kt = slot_key[t];
+            rank += (kt < key) || (kt == key && slot_id[t] < id);
+        }
+    } else {
+        for (int t = b; t < e; ++t) rank += (slot_id[t] < id);
+    }
     const int dst = b + rank;
 
     if (apply_kick) {
@@ -297,7 +317,6 @@ k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict
             v.x *= k; v.y *= k; v.z *= k;
         }
     }
-    const float4 p = posw_in[i];
     posw_out[dst] = p;
     veli_out[dst] = v;
     cell_sorted[dst] = c;

@@ -278,12 +278,15 @@ __device__ __forceinline__ bool needs_repair(const Geometry& g, float d2)
     return (!(d2 < g.r2_lo) && d2 < g.r2_hi) || d2 <= 1e-10f;
 }
 
-__device__ __forceinline__ void repair(Home& h, const PairParam* __restrict__ tabrow,
+// The corrections of a run are summed apart from its main chain of fused multiply-adds and added
+// at its end: a particle's result must not depend on how the candidates were grouped in fours,
+// which differs between the per-lane walk and the culled walk of a whole warp.
+__device__ __forceinline__ void repair(float3& rep, const Home& h, const PairParam* __restrict__ tabrow,
                                        const Geometry& g, const Image& im, const float4 pj)
 {
     const float3 f = repair_pair_clusters(g, h.x, h.y, h.z, im.x, im.y, im.z, im.lx, im.ly, im.lz,
                                           im.shifts, pj.x, pj.y, pj.z, tabrow + __float_as_int(pj.w));
-    h.ax += f.x; h.ay += f.y; h.az += f.z;
+    rep.x += f.x; rep.y += f.y; rep.z += f.z;
 }
 
 // ---- systems with Boids-kind pairs: deferred interactions ----------------------------------
@@ -413,6 +416,7 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
     // the run sums into its own accumulator (shorter partial sums: less fp32 rounding)
     const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
     h.ax = h.ay = h.az = 0.0f;
+    float3 rep = make_float3(0.0f, 0.0f, 0.0f);
     const unsigned tag = (unsigned)im.shifts << kQueueSlotBits;
     int j = s;
     for (; j + 4 <= e; j += 4) {
@@ -443,10 +447,10 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
                        b2 = !(d2 < g.r2_lo) && d2 < g.r2_hi, b3 = !(d3 < g.r2_lo) && d3 < g.r2_hi;
             const bool tiny = fminf(fminf(d0, d1), fminf(d2, d3)) <= 1e-10f;
             if (b0 | b1 | b2 | b3 | tiny) {
-                if (needs_repair(g, d0)) repair(h, tabrow, g, im, p0);
-                if (needs_repair(g, d1)) repair(h, tabrow, g, im, p1);
-                if (needs_repair(g, d2)) repair(h, tabrow, g, im, p2);
-                if (needs_repair(g, d3)) repair(h, tabrow, g, im, p3);
+                if (needs_repair(g, d0)) repair(rep, h, tabrow, g, im, p0);
+                if (needs_repair(g, d1)) repair(rep, h, tabrow, g, im, p1);
+                if (needs_repair(g, d2)) repair(rep, h, tabrow, g, im, p2);
+                if (needs_repair(g, d3)) repair(rep, h, tabrow, g, im, p3);
             }
         }
     }
@@ -454,13 +458,143 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
         const float4 pj = ldg4(a.posw + j);
         if (KIND == kKindBoids) pair_note<LOWFIX>(g, im, pj, tag | (unsigned)j, q);
         else if (KIND == kKindMixed) pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j, pj);
-        else if (needs_repair(g, pair_clusters<LOWFIX>(h, tabrow_s, g, im, pj))) repair(h, tabrow, g, im, pj);
+        else if (needs_repair(g, pair_clusters<LOWFIX>(h, tabrow_s, g, im, pj))) repair(rep, h, tabrow, g, im, pj);
     }
     if (KIND == kKindBoids) {
         // (the tail added at most three entries: room for the next group of four is kept here)
         if (__any_sync(__activemask(), q.count > kQueueDepth - 4)) drain(q, h, tabrow, boid_acc, a, g);
     }
+    if (KIND == kKindClusters) { h.ax += rep.x; h.ay += rep.y; h.az += rep.z; }
     h.ax += ax0; h.ay += ay0; h.az += az0;
+}
+
+// ---- Clusters kind: one walk for the whole warp, culled against the box of its home particles --
+// When the 32 home particles of a warp sit in one row of cells (same y and z cell), the union of
+// their runs is itself one contiguous run per stencil row, and the warp can walk it as one: every
+// lane meets a superset of its own candidates in the same order, and the extra ones are farther
+// than one bin (>= r_max) from it, i.e. add exactly zero.  What this buys is warp-uniform control
+// flow, which makes culling possible: about half of the candidates are out of range for EVERY
+// lane.  Per chunk of 32 candidates each lane tests ONE against the box of the warp's home
+// particles, the votes are collected with a ballot, and only the surviving candidates are
+// evaluated, four at a time as in the per-lane walk.  A skipped candidate would have added exactly zero, so a particle's result
+// does not depend on which walk its warp takes.
+struct Box { float lox, loy, loz, hix, hiy, hiz; };
+
+__device__ __forceinline__ Box warp_box(const Home& h)
+{
+    // coordinates are >= 0: their bit patterns order like the values
+    const unsigned ux = __float_as_uint(fabsf(h.x)), uy = __float_as_uint(fabsf(h.y)), uz = __float_as_uint(fabsf(h.z));
+    Box b;
+    b.lox = __uint_as_float(__reduce_min_sync(0xffffffffu, ux));
+    b.loy = __uint_as_float(__reduce_min_sync(0xffffffffu, uy));
+    b.loz = __uint_as_float(__reduce_min_sync(0xffffffffu, uz));
+    b.hix = __uint_as_float(__reduce_max_sync(0xffffffffu, ux));
+    b.hiy = __uint_as_float(__reduce_max_sync(0xffffffffu, uy));
+    b.hiz = __uint_as_float(__reduce_max_sync(0xffffffffu, uz));
+    return b;
+}
+
+constexpr int kListLen = 64;  // survivors a warp can hold: fewer than 4 left over + 32 of a chunk
+
+__device__ __forceinline__ void sts4(unsigned saddr, const float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float4 lds4v(unsigned saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(saddr)
+                 : "memory");
+    return v;
+}
+
+// four survivors from the warp's list (one broadcast 16-byte shared-memory load each)
+template <bool LOWFIX>
+__device__ __forceinline__ void walk_group(Home& h, float3& rep, RowAddr tabrow_s,
+                                           const PairParam* __restrict__ tabrow, const Geometry& g,
+                                           const Image& im, unsigned at)
+{
+    const float4 p0 = lds4v(at), p1 = lds4v(at + 16u), p2 = lds4v(at + 32u), p3 = lds4v(at + 48u);
+    const float d0 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p0);
+    const float d1 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p1);
+    const float d2 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p2);
+    const float d3 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p3);
+    const bool b0 = !(d0 < g.r2_lo) && d0 < g.r2_hi, b1 = !(d1 < g.r2_lo) && d1 < g.r2_hi,
+               b2 = !(d2 < g.r2_lo) && d2 < g.r2_hi, b3 = !(d3 < g.r2_lo) && d3 < g.r2_hi;
+    const bool tiny = fminf(fminf(d0, d1), fminf(d2, d3)) <= 1e-10f;
+    if (b0 | b1 | b2 | b3 | tiny) {
+        if (needs_repair(g, d0)) repair(rep, h, tabrow, g, im, p0);
+        if (needs_repair(g, d1)) repair(rep, h, tabrow, g, im, p1);
+        if (needs_repair(g, d2)) repair(rep, h, tabrow, g, im, p2);
+        if (needs_repair(g, d3)) repair(rep, h, tabrow, g, im, p3);
+    }
+}
+
+// `lst`: shared-memory address of the warp's survivor list (kListLen float4, a ring).  Per chunk
+// of 32 candidates every lane loads one and tests it against the box; the survivors are appended
+// in order (ballot + prefix count), and the list is consumed four at a time, left-overs carried
+// to the next chunk.  The run's last group is padded with a particle parked far outside the box.
+template <bool LOWFIX>
+__device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
+                                            const ForceArgs& a, const Geometry& g, const Image& im,
+                                            const Box& b, int sx, int sy, int sz, int s, int e, unsigned lst)
+{
+    // the run sums into its own accumulator (shorter partial sums: less fp32 rounding)
+    const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+    h.ax = h.ay = h.az = 0.0f;
+    float3 rep = make_float3(0.0f, 0.0f, 0.0f);
+    // the box as this run sees it (the periodic shift is the same for all lanes)
+    const float tx = sx * g.Lx, ty = sy * g.Ly, tz = sz * g.Lz;
+    const float lox = b.lox + tx - g.cull_slack, hix = b.hix + tx + g.cull_slack;
+    const float loy = b.loy + ty - g.cull_slack, hiy = b.hiy + ty + g.cull_slack;
+    const float loz = b.loz + tz - g.cull_slack, hiz = b.hiz + tz + g.cull_slack;
+    const unsigned lane = (unsigned)lane_id(), below = (1u << lane) - 1u;
+    unsigned head = 0u, len = 0u;  // warp-uniform; head stays a multiple of four
+    for (int base = s; base < e; base += 32) {
+        const int jl = base + (int)lane;
+        bool keep = false;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jl < e) {
+            p = ldg4(a.posw + jl);
+            const float ex = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
+            const float ey = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
+            const float ez = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
+            keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < g.cull_r2;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) sts4(lst + (((head + len + __popc(m & below)) & (kListLen - 1)) << 4), p);
+        len += __popc(m);
+        __syncwarp();
+        while (len >= 4u) {
+            walk_group<LOWFIX>(h, rep, tabrow_s, tabrow, g, im, lst + ((head & (kListLen - 1)) << 4));
+            head += 4u;
+            len -= 4u;
+        }
+        __syncwarp();  // the list is read before the next chunk appends to it
+    }
+    if (len > 0u) {
+        if (lane < 4u - len)
+            sts4(lst + (((head + len + lane) & (kListLen - 1)) << 4), make_float4(kDummyPos, kDummyPos, kDummyPos, 0.0f));
+        __syncwarp();
+        walk_group<LOWFIX>(h, rep, tabrow_s, tabrow, g, im, lst + ((head & (kListLen - 1)) << 4));
+        __syncwarp();
+    }
+    h.ax += rep.x; h.ay += rep.y; h.az += rep.z;
+    h.ax += ax0; h.ay += ay0; h.az += az0;
+}
+
+__device__ __forceinline__ void walk_image(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
+                                           const ForceArgs& a, const Geometry& g, const Box& b,
+                                           int sx, int sy, int sz, int s, int e, unsigned lst)
+{
+    const Image im = make_image(h, g, sx, sy, sz);
+    if (__any_sync(0xffffffffu, im.up))
+        walk_culled<true>(h, tabrow_s, tabrow, a, g, im, b, sx, sy, sz, s, e, lst);
+    else
+        walk_culled<false>(h, tabrow_s, tabrow, a, g, im, b, sx, sy, sz, s, e, lst);
 }
 
 // Choice of the LOWFIX variant for the lanes that are converged here (every lane of a code
@@ -743,6 +877,11 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     float2* tabB = reinterpret_cast<float2*>(tabA + T * TA);
     float* boid_acc = reinterpret_cast<float*>(tabB + T * TA + (T * TA & 1)) + threadIdx.x;
     float* part = reinterpret_cast<float*>(tabB + T * TA + (T * TA & 1)) + hl;  // SPLIT > 1 only
+    // Clusters kind: every warp's list of surviving candidates (walk_culled), behind `part`
+    const unsigned lst = (unsigned)__cvta_generic_to_shared(
+                             reinterpret_cast<float4*>(tabB + T * TA + (T * TA & 1)) +
+                             (SPLIT > 1 ? kSplitRuns * 3 * kSplitHomes / 4 : 0)) +
+                         (threadIdx.x >> 5) * (kListLen * 16u);
     for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
         const PairParam pp = a.table[q];
         tab[q] = pp;
@@ -811,7 +950,63 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     const bool quirk = g.is3d && a.wrap_mode == kWrapReference && (gz == 0 || gz == g.nbz - 1);
 
     const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
-    if (!quirk) {
+    // Clusters kind: the whole warp walks as one when its home particles share a row of cells and
+    // none is on the literal z-wrap path (all lanes are converged here, padding lanes included:
+    // they repeat the last particle and store nothing).
+    bool as_warp = false;
+#ifndef GOF_NO_WARP_WALK
+    if (KIND == kKindClusters)
+        as_warp = __all_sync(0xffffffffu, !quirk) &&
+                  __reduce_min_sync(0xffffffffu, (unsigned)cyz) == __reduce_max_sync(0xffffffffu, (unsigned)cyz);
+#endif
+    if (as_warp) {
+        const Box box = warp_box(h);
+        const int cx_min = (int)__reduce_min_sync(0xffffffffu, (unsigned)cx);
+        const int cx_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)cx);
+        int row = 0;
+        for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
+            int nl = lz + dzi, sz = 0;
+            if (g.is3d) {
+                const int ngz = gz + dzi;
+                if (ngz < 0) { sz = 1; if (g.index_wrap_z) nl += g.nbz; }
+                else if (ngz >= g.nbz) { sz = -1; if (g.index_wrap_z) nl -= g.nbz; }
+            }
+            for (int dyi = -1; dyi <= 1; ++dyi, ++row) {
+                if (SPLIT > 1 && row / rows_per_share != share) continue;
+                int ny = cy + dyi, sy = 0;
+                if (ny < 0) { ny += g.nby; sy = 1; }
+                else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
+                const int rb = (nl * g.nby + ny) * g.nbx;
+                // the union of the lanes' un-shifted runs: cells cx_min - 1 .. cx_max + 1 of the row
+                const int lo = cx_min > 0 ? cx_min - 1 : 0;
+                const int hi = cx_max < g.nbx - 1 ? cx_max + 1 : g.nbx - 1;
+                walk_image(h, tabrow_s, tabrow, a, g, box, 0, sy, sz, a.pstart[rb + lo],
+                           a.pstart[rb + hi] + a.count[rb + hi], lst);
+                if (SPLIT > 1) {
+                    store_partial(part, 2 * row, h);
+                    h.ax = h.ay = h.az = 0.0f;
+                }
+                // the cells across the periodic x boundary, for the lanes in the first / last cell of
+                // the row (the shifted image of any other lane is more than a bin away from them)
+                const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+                h.ax = h.ay = h.az = 0.0f;
+                if (cx_min == 0) {
+                    const int s = a.pstart[rb + g.nbx - 1];
+                    walk_image(h, tabrow_s, tabrow, a, g, box, 1, sy, sz, s, s + a.count[rb + g.nbx - 1], lst);
+                }
+                if (cx_max == g.nbx - 1) {
+                    const int s = a.pstart[rb];
+                    walk_image(h, tabrow_s, tabrow, a, g, box, -1, sy, sz, s, s + a.count[rb], lst);
+                }
+                if (SPLIT > 1) {
+                    store_partial(part, 2 * row + 1, h);
+                    h.ax = h.ay = h.az = 0.0f;
+                } else {
+                    h.ax += ax0; h.ay += ay0; h.az += az0;
+                }
+            }
+        }
+    } else if (!quirk) {
         int row = 0;
         for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
             int nl = lz + dzi, sz = 0;

@@ -49,6 +49,9 @@ struct Geometry {
     float Lx, Ly, Lz, rmax;
     float Lx_lo, Ly_lo, Lz_lo;  // what (float)L lost: L = L + L_lo to ~2^-48 (exact periodic images)
     float r2_lo, r2_hi;  // guard band around r_max^2: inside it the cut-off is re-decided in float64
+    // warp-level culling of candidates against the box of a warp's home particles: a candidate
+    // farther than sqrt(cull_r2) from the box grown by cull_slack is out of range for all of them
+    float cull_r2, cull_slack;
     // thresholds of the reference's z-wrap tests, pre-rounded so that fp32 comparisons of fp32
     // coordinates decide exactly like the reference's float64 ones:
     //   z < r_max  <=>  z < zq_r     (zq_r   = smallest float >= r_max)
