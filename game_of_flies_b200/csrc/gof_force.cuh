@@ -272,10 +272,14 @@ __device__ __forceinline__ float pair_clusters(Home& h, RowAddr tabrow_s, const 
     return d2;
 }
 
-// needs the cold path: in the guard band, or at/below the reference's 1e-10 bound
+// needs the cold path: in the guard band, or at/below the reference's 1e-10 bound -- except at
+// distance exactly zero (the particle itself, met once by every particle): the hot loop added
+// s * 0 = 0 there, which is what the reference's lower bound yields, so nothing is to be repaired
+// (the cold path is ~100 instructions with one lane active: 10 % of the kernel when it was taken
+// for every self pair).
 __device__ __forceinline__ bool needs_repair(const Geometry& g, float d2)
 {
-    return (!(d2 < g.r2_lo) && d2 < g.r2_hi) || d2 <= 1e-10f;
+    return (!(d2 < g.r2_lo) && d2 < g.r2_hi) || (d2 <= 1e-10f && d2 > 0.0f);
 }
 
 // The corrections of a run are summed apart from its main chain of fused multiply-adds and added
