@@ -290,7 +290,7 @@ static size_t force_smem_bytes(int T, int kind, int split)
            (kind != kKindClusters ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0) +
            (kind == kKindBoids ? (size_t)kQueueDepth * kForceThreads * sizeof(unsigned) : 0) +
            (split > 1 ? (size_t)kSplitRuns * 3 * kSplitHomes * sizeof(float) : 0) +
-           (kind == kKindClusters ? (size_t)(split > 1 ? split : kForceThreads / 32) * kListLen * sizeof(float4) : 0);
+           (kind == kKindClusters ? (size_t)(split > 1 ? split : kForceThreads / 32) * kListLen * (sizeof(float4) + sizeof(int)) : 0);
 }
 
 template <int KIND, int MODE, int SPLIT>

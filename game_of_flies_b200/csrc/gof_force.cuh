@@ -15,6 +15,7 @@
 // cell, so all lanes of a warp read the same neighbour at the same time (one
 // 16-byte broadcast load served by L1).
 #pragma once
+#include <climits>
 #include "gof_binning.cuh"
 
 namespace gof {
@@ -472,6 +473,13 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
     h.ax += ax0; h.ay += ay0; h.az += az0;
 }
 
+// (the literal z-wrap pair of the Clusters kind and its cold path are defined further down)
+__device__ __forceinline__ float pair_clusters_quirk(Home& h, RowAddr tabrow_s, const Geometry& g,
+                                                     const Image& im, bool direct, const float4 pj);
+__device__ __forceinline__ void repair_quirk(float3& rep, const Home& h, const PairParam* __restrict__ tabrow,
+                                             const Geometry& g, const Image& im, int sx, int sy, bool direct,
+                                             const float4 pj);
+
 // ---- Clusters kind: one walk for the whole warp, culled against the box of its home particles --
 // When the 32 home particles of a warp sit in one row of cells (same y and z cell), the union of
 // their runs is itself one contiguous run per stencil row, and the warp can walk it as one: every
@@ -515,25 +523,47 @@ __device__ __forceinline__ float4 lds4v(unsigned saddr)
     return v;
 }
 
-// four survivors from the warp's list (one broadcast 16-byte shared-memory load each)
-template <bool LOWFIX>
+// four survivors from the warp's list (one broadcast 16-byte shared-memory load each).
+// LITERAL: the home cells are in the bottom / top layer in GOF_WRAP_REFERENCE mode; the pair is
+// evaluated by the literal z-wrap rules, in the role (`direct` or not, see quirk_home) that follows
+// from the survivor's slot `at_j` against the threshold `own` of the lane.
+template <bool LITERAL, bool LOWFIX>
 __device__ __forceinline__ void walk_group(Home& h, float3& rep, RowAddr tabrow_s,
                                            const PairParam* __restrict__ tabrow, const Geometry& g,
-                                           const Image& im, unsigned at)
+                                           const Image& im, unsigned at, unsigned at_j, int own, int sx, int sy)
 {
     const float4 p0 = lds4v(at), p1 = lds4v(at + 16u), p2 = lds4v(at + 32u), p3 = lds4v(at + 48u);
-    const float d0 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p0);
-    const float d1 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p1);
-    const float d2 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p2);
-    const float d3 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p3);
+    float d0, d1, d2, d3;
+    bool r0 = true, r1 = true, r2 = true, r3 = true;
+    if (LITERAL) {
+        const float4 jj = lds4v(at_j);
+        r0 = __float_as_int(jj.x) >= own; r1 = __float_as_int(jj.y) >= own;
+        r2 = __float_as_int(jj.z) >= own; r3 = __float_as_int(jj.w) >= own;
+        d0 = pair_clusters_quirk(h, tabrow_s, g, im, r0, p0);
+        d1 = pair_clusters_quirk(h, tabrow_s, g, im, r1, p1);
+        d2 = pair_clusters_quirk(h, tabrow_s, g, im, r2, p2);
+        d3 = pair_clusters_quirk(h, tabrow_s, g, im, r3, p3);
+    } else {
+        d0 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p0);
+        d1 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p1);
+        d2 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p2);
+        d3 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p3);
+    }
     const bool b0 = !(d0 < g.r2_lo) && d0 < g.r2_hi, b1 = !(d1 < g.r2_lo) && d1 < g.r2_hi,
                b2 = !(d2 < g.r2_lo) && d2 < g.r2_hi, b3 = !(d3 < g.r2_lo) && d3 < g.r2_hi;
     const bool tiny = fminf(fminf(d0, d1), fminf(d2, d3)) <= 1e-10f;
     if (b0 | b1 | b2 | b3 | tiny) {
-        if (needs_repair(g, d0)) repair(rep, h, tabrow, g, im, p0);
-        if (needs_repair(g, d1)) repair(rep, h, tabrow, g, im, p1);
-        if (needs_repair(g, d2)) repair(rep, h, tabrow, g, im, p2);
-        if (needs_repair(g, d3)) repair(rep, h, tabrow, g, im, p3);
+        if (LITERAL) {
+            if (needs_repair(g, d0)) repair_quirk(rep, h, tabrow, g, im, sx, sy, r0, p0);
+            if (needs_repair(g, d1)) repair_quirk(rep, h, tabrow, g, im, sx, sy, r1, p1);
+            if (needs_repair(g, d2)) repair_quirk(rep, h, tabrow, g, im, sx, sy, r2, p2);
+            if (needs_repair(g, d3)) repair_quirk(rep, h, tabrow, g, im, sx, sy, r3, p3);
+        } else {
+            if (needs_repair(g, d0)) repair(rep, h, tabrow, g, im, p0);
+            if (needs_repair(g, d1)) repair(rep, h, tabrow, g, im, p1);
+            if (needs_repair(g, d2)) repair(rep, h, tabrow, g, im, p2);
+            if (needs_repair(g, d3)) repair(rep, h, tabrow, g, im, p3);
+        }
     }
 }
 
@@ -541,10 +571,14 @@ __device__ __forceinline__ void walk_group(Home& h, float3& rep, RowAddr tabrow_
 // of 32 candidates every lane loads one and tests it against the box; the survivors are appended
 // in order (ballot + prefix count), and the list is consumed four at a time, left-overs carried
 // to the next chunk.  The run's last group is padded with a particle parked far outside the box.
-template <bool LOWFIX>
+//
+// LITERAL: `im` carries no z shift; the z separation of a pair is whatever the literal rules make
+// it, so a candidate survives if it is in reach of the box as it is or one box length up or down.
+template <bool LITERAL, bool LOWFIX>
 __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
                                             const ForceArgs& a, const Geometry& g, const Image& im,
-                                            const Box& b, int sx, int sy, int sz, int s, int e, unsigned lst)
+                                            const Box& b, int sx, int sy, int sz, int s, int e, unsigned lst,
+                                            unsigned lst_j, int own)
 {
     // the run sums into its own accumulator (shorter partial sums: less fp32 rounding)
     const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
@@ -565,25 +599,39 @@ __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const Pai
             p = ldg4(a.posw + jl);
             const float ex = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
             const float ey = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
-            const float ez = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
+            float ez = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
+            if (LITERAL) {
+                const float up = fmaxf(fmaxf((loz + g.Lz) - p.z, p.z - (hiz + g.Lz)), 0.0f);
+                const float dn = fmaxf(fmaxf((loz - g.Lz) - p.z, p.z - (hiz - g.Lz)), 0.0f);
+                ez = fminf(ez, fminf(up, dn));
+            }
             keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < g.cull_r2;
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) sts4(lst + (((head + len + __popc(m & below)) & (kListLen - 1)) << 4), p);
+        if (keep) {
+            const unsigned at = (head + len + __popc(m & below)) & (kListLen - 1);
+            sts4(lst + (at << 4), p);
+            if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (at << 2)), "r"(jl) : "memory");
+        }
         len += __popc(m);
         __syncwarp();
         while (len >= 4u) {
-            walk_group<LOWFIX>(h, rep, tabrow_s, tabrow, g, im, lst + ((head & (kListLen - 1)) << 4));
+            const unsigned at = head & (kListLen - 1);
+            walk_group<LITERAL, LOWFIX>(h, rep, tabrow_s, tabrow, g, im, lst + (at << 4), lst_j + (at << 2), own, sx, sy);
             head += 4u;
             len -= 4u;
         }
         __syncwarp();  // the list is read before the next chunk appends to it
     }
     if (len > 0u) {
-        if (lane < 4u - len)
-            sts4(lst + (((head + len + lane) & (kListLen - 1)) << 4), make_float4(kDummyPos, kDummyPos, kDummyPos, 0.0f));
+        if (lane < 4u - len) {
+            const unsigned at = (head + len + lane) & (kListLen - 1);
+            sts4(lst + (at << 4), make_float4(kDummyPos, kDummyPos, kDummyPos, 0.0f));
+            if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (at << 2)), "r"(0) : "memory");
+        }
         __syncwarp();
-        walk_group<LOWFIX>(h, rep, tabrow_s, tabrow, g, im, lst + ((head & (kListLen - 1)) << 4));
+        const unsigned at = head & (kListLen - 1);
+        walk_group<LITERAL, LOWFIX>(h, rep, tabrow_s, tabrow, g, im, lst + (at << 4), lst_j + (at << 2), own, sx, sy);
         __syncwarp();
     }
     h.ax += rep.x; h.ay += rep.y; h.az += rep.z;
@@ -596,9 +644,9 @@ __device__ __forceinline__ void walk_image(Home& h, RowAddr tabrow_s, const Pair
 {
     const Image im = make_image(h, g, sx, sy, sz);
     if (__any_sync(0xffffffffu, im.up))
-        walk_culled<true>(h, tabrow_s, tabrow, a, g, im, b, sx, sy, sz, s, e, lst);
+        walk_culled<false, true>(h, tabrow_s, tabrow, a, g, im, b, sx, sy, sz, s, e, lst, 0u, 0);
     else
-        walk_culled<false>(h, tabrow_s, tabrow, a, g, im, b, sx, sy, sz, s, e, lst);
+        walk_culled<false, false>(h, tabrow_s, tabrow, a, g, im, b, sx, sy, sz, s, e, lst, 0u, 0);
 }
 
 // Choice of the LOWFIX variant for the lanes that are converged here (every lane of a code
@@ -697,36 +745,61 @@ __device__ __noinline__ float3 repair_quirk_clusters(const Geometry& g, bool dir
     return make_float3(-s * dx, -s * dy, -s * dz);
 }
 
-template <bool BOIDS>
-__device__ __forceinline__ void quirk_pair(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
-                                           float* __restrict__ boid_acc, const ForceArgs& a,
-                                           const Geometry& g, const Image& im, int sx, int sy, bool direct,
-                                           int j, const float4 pj)
+// Literal pair of the Clusters kind, branch-free like pair_clusters: force for every candidate,
+// masked by the cut-off; returns d2 so that the caller can spot the pairs that need the cold path.
+__device__ __forceinline__ float pair_clusters_quirk(Home& h, RowAddr tabrow_s, const Geometry& g,
+                                                     const Image& im, bool direct, const float4 pj)
 {
     float dz, relz;
     quirk_dz(g, direct, h.z, h.y, pj.z, pj.y, dz, relz);
     const float dx = (im.x - pj.x) + im.lx, dy = (im.y - pj.y) + im.ly;
     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const unsigned tj = (unsigned)__float_as_int(pj.w);
+    const float4 qa = lds4(tabrow_s.a + tj * 16u);
+    const float2 qb = lds2(tabrow_s.b + tj * 8u);
+    const float inv = fast_rsqrt(d2 + kTinyD2);
+    const float dist = d2 * inv;
+    const float f_in = fmaf(-qa.y, dist, qa.z);
+    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+    float s = (dist < qa.x ? f_in : f_tri) * inv;
+    s = d2 < g.r2_lo ? s : 0.0f;
+    h.ax = fmaf(-s, dx, h.ax);
+    h.ay = fmaf(-s, dy, h.ay);
+    h.az = fmaf(-s, dz, h.az);
+    return d2;
+}
+
+// its cold path; like `repair`, the corrections of a run are summed apart (`rep`)
+__device__ __forceinline__ void repair_quirk(float3& rep, const Home& h, const PairParam* __restrict__ tabrow,
+                                             const Geometry& g, const Image& im, int sx, int sy, bool direct,
+                                             const float4 pj)
+{
+    float dz, relz;
+    quirk_dz(g, direct, h.z, h.y, pj.z, pj.y, dz, relz);
+    const float dx = (im.x - pj.x) + im.lx, dy = (im.y - pj.y) + im.ly;
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float3 f = repair_quirk_clusters(g, direct, h.x, h.y, h.z, pj.x, pj.y, pj.z, sx, sy, dx, dy, dz, d2,
+                                           tabrow + __float_as_int(pj.w));
+    rep.x += f.x; rep.y += f.y; rep.z += f.z;
+}
+
+template <bool BOIDS>
+__device__ __forceinline__ void quirk_pair(Home& h, float3& rep, RowAddr tabrow_s,
+                                           const PairParam* __restrict__ tabrow,
+                                           float* __restrict__ boid_acc, const ForceArgs& a,
+                                           const Geometry& g, const Image& im, int sx, int sy, bool direct,
+                                           int j, const float4 pj)
+{
     if (!BOIDS) {
-        // branch-free like pair_clusters: force for every candidate, masked by the cut-off
-        const unsigned tj = (unsigned)__float_as_int(pj.w);
-        const float4 qa = lds4(tabrow_s.a + tj * 16u);
-        const float2 qb = lds2(tabrow_s.b + tj * 8u);
-        const float inv = fast_rsqrt(d2 + kTinyD2);
-        const float dist = d2 * inv;
-        const float f_in = fmaf(-qa.y, dist, qa.z);
-        const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-        float s = (dist < qa.x ? f_in : f_tri) * inv;
-        s = d2 < g.r2_lo ? s : 0.0f;
-        h.ax = fmaf(-s, dx, h.ax);
-        h.ay = fmaf(-s, dy, h.ay);
-        h.az = fmaf(-s, dz, h.az);
-        if (needs_repair(g, d2)) {
-            const float3 f = repair_quirk_clusters(g, direct, h.x, h.y, h.z, pj.x, pj.y, pj.z, sx, sy, dx, dy,
-                                                   dz, d2, tabrow + tj);
-            h.ax += f.x; h.ay += f.y; h.az += f.z;
-        }
-    } else if (d2 < g.r2_hi && d2 > 1e-10f) {
+        if (needs_repair(g, pair_clusters_quirk(h, tabrow_s, g, im, direct, pj)))
+            repair_quirk(rep, h, tabrow, g, im, sx, sy, direct, pj);
+        return;
+    }
+    float dz, relz;
+    quirk_dz(g, direct, h.z, h.y, pj.z, pj.y, dz, relz);
+    const float dx = (im.x - pj.x) + im.lx, dy = (im.y - pj.y) + im.ly;
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (d2 < g.r2_hi && d2 > 1e-10f) {
         const float hx = h.x, hy = h.y, hz = h.z;
         auto exact = [&]() { return quirk_exact_d2(g, direct, hx, hy, hz, pj.x, pj.y, pj.z, sx, sy); };
         bool ok = true;
@@ -741,7 +814,8 @@ __device__ __forceinline__ void quirk_pair(Home& h, RowAddr tabrow_s, const Pair
 }
 
 template <bool BOIDS>
-__device__ __forceinline__ void run_pairs_zquirk(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
+__device__ __forceinline__ void run_pairs_zquirk(Home& h, float3& rep, RowAddr tabrow_s,
+                                              const PairParam* __restrict__ tabrow,
                                               float* __restrict__ boid_acc, const ForceArgs& a,
                                               const Geometry& g, int s, int e, int sx, int sy,
                                               bool direct)
@@ -751,13 +825,13 @@ __device__ __forceinline__ void run_pairs_zquirk(Home& h, RowAddr tabrow_s, cons
     for (; j + 4 <= e; j += 4) {
         const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
                      p3 = ldg4(a.posw + j + 3);
-        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j, p0);
-        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 1, p1);
-        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 2, p2);
-        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 3, p3);
+        quirk_pair<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j, p0);
+        quirk_pair<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 1, p1);
+        quirk_pair<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 2, p2);
+        quirk_pair<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j + 3, p3);
     }
     for (; j < e; ++j)
-        quirk_pair<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j, ldg4(a.posw + j));
+        quirk_pair<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, im, sx, sy, direct, j, ldg4(a.posw + j));
 }
 
 // Split kernel: run q's partial sum of this warp's home particle, [run][component][home lane].
@@ -810,6 +884,7 @@ __device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type
             const int hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
             float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
             h.ax = h.ay = h.az = 0.0f;
+            float3 rep = make_float3(0.0f, 0.0f, 0.0f);  // guard-band corrections of the run (Clusters kind)
             // Half stencil of set_bin_neighbours (acceleration_updater.py:140-215): the home particle
             // is the reference's thread i ("direct") for the upper layer, for the row above in its own
             // layer, and for its own cell and the next one in x; elsewhere the neighbour is.  Only the
@@ -818,31 +893,108 @@ __device__ __noinline__ float3 quirk_home(float hx, float hy, float hz, int type
                 if (lo < cx) {
                     const int s = a.pstart[rb + lo];
                     const int e = valid ? s + a.count[rb + lo] : s;
-                    run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, false);
+                    run_pairs_zquirk<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, false);
                 }
                 const int s = a.pstart[rb + cx];
                 const int e = valid ? a.pstart[rb + hi] + a.count[rb + hi] : s;
-                run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, true);
+                run_pairs_zquirk<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, true);
             } else {
                 const bool direct = dzi == 1 || (dzi == 0 && dyi == 1);
                 const int s = a.pstart[rb + lo];
                 const int e = valid ? a.pstart[rb + hi] + a.count[rb + hi] : s;
-                run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, direct);
+                run_pairs_zquirk<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, s, e, 0, sy, direct);
             }
+            if (!BOIDS) { h.ax += rep.x; h.ay += rep.y; h.az += rep.z; }
             if (SPLIT > 1) store_partial(part, 2 * row, h);
             h.ax += ax0; h.ay += ay0; h.az += az0;
             ax0 = h.ax; ay0 = h.ay; az0 = h.az;
             h.ax = h.ay = h.az = 0.0f;
+            rep = make_float3(0.0f, 0.0f, 0.0f);
             if (cx == 0 || cx == g.nbx - 1) {
                 const int wc = cx == 0 ? g.nbx - 1 : 0;
                 const int dxi = cx == 0 ? -1 : 1;
                 const bool direct = dzi == 1 || (dzi == 0 && (dyi == 1 || (dyi == 0 && dxi >= 0)));
                 const int s = a.pstart[rb + wc];
                 const int e = valid ? s + a.count[rb + wc] : s;
-                run_pairs_zquirk<BOIDS>(h, tabrow_s, tabrow, boid_acc, a, g, s, e, cx == 0 ? 1 : -1, sy, direct);
+                run_pairs_zquirk<BOIDS>(h, rep, tabrow_s, tabrow, boid_acc, a, g, s, e, cx == 0 ? 1 : -1, sy, direct);
             }
+            if (!BOIDS) { h.ax += rep.x; h.ay += rep.y; h.az += rep.z; }
             if (SPLIT > 1) store_partial(part, 2 * row + 1, h);
             h.ax += ax0; h.ay += ay0; h.az += az0;
+        }
+    }
+    return make_float3(h.ax, h.ay, h.az);
+}
+
+// The whole-warp walk of a warp whose home cells are in the bottom / top layer in
+// GOF_WRAP_REFERENCE mode (Clusters kind): rows and runs as in k_force's walk, pairs by the
+// literal rules.  The role of a pair -- is the home particle the reference's thread i
+// ("direct")? -- follows from the stencil row, and in the home row from the candidate's cell
+// against the lane's own (see quirk_home): direct <=> the candidate's slot >= `own`.  Out of line:
+// the common walk keeps its register allocation.
+template <int SPLIT>
+__device__ __noinline__ float3 quirk_walk(float hx, float hy, float hz, int type, RowAddr tabrow_s,
+                                          const PairParam* __restrict__ tabrow, const ForceArgs& a,
+                                          const Geometry& g, float lox, float loy, float loz, float hix,
+                                          float hiy, float hiz, int cx, int cy, int lz, int gz, int cx_min,
+                                          int cx_max, unsigned lst, unsigned lst_j, int share, int rows_per_share,
+                                          float* __restrict__ part)
+{
+    Home h;
+    h.x = hx; h.y = hy; h.z = hz;
+    h.vx = h.vy = h.vz = 0.0f;
+    h.ax = h.ay = h.az = 0.0f;
+    h.type = type;
+    h.kinds = 0u;
+    Box box;
+    box.lox = lox; box.loy = loy; box.loz = loz; box.hix = hix; box.hiy = hiy; box.hiz = hiz;
+    const int all = INT_MIN, none = INT_MAX;
+    int row = 0;
+    for (int dzi = -1; dzi <= 1; ++dzi) {
+        int nl = lz + dzi;
+        const int ngz = gz + dzi;
+        if (g.index_wrap_z) {
+            if (ngz < 0) nl += g.nbz;
+            else if (ngz >= g.nbz) nl -= g.nbz;
+        }
+        for (int dyi = -1; dyi <= 1; ++dyi, ++row) {
+            if (SPLIT > 1 && row / rows_per_share != share) continue;
+            int ny = cy + dyi, sy = 0;
+            if (ny < 0) { ny += g.nby; sy = 1; }
+            else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
+            const int rb = (nl * g.nby + ny) * g.nbx;
+            const int lo = cx_min > 0 ? cx_min - 1 : 0;
+            const int hi = cx_max < g.nbx - 1 ? cx_max + 1 : g.nbx - 1;
+            const bool row_direct = dzi == 1 || (dzi == 0 && dyi == 1);
+            const bool home_row = dzi == 0 && dyi == 0;
+            {
+                const Image im = make_image(h, g, 0, sy, 0);
+                walk_culled<true, true>(h, tabrow_s, tabrow, a, g, im, box, 0, sy, 0, a.pstart[rb + lo],
+                                        a.pstart[rb + hi] + a.count[rb + hi], lst, lst_j,
+                                        home_row ? a.pstart[rb + cx] : (row_direct ? all : none));
+            }
+            if (SPLIT > 1) {
+                store_partial(part, 2 * row, h);
+                h.ax = h.ay = h.az = 0.0f;
+            }
+            const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+            h.ax = h.ay = h.az = 0.0f;
+            for (int side = 0; side < 2; ++side) {
+                // side 0: the home's x - 1 neighbour across the boundary; side 1: its x + 1 neighbour
+                if (side == 0 ? cx_min != 0 : cx_max != g.nbx - 1) continue;
+                const int wc = side == 0 ? g.nbx - 1 : 0, sx = side == 0 ? 1 : -1;
+                const bool direct = row_direct || (home_row && side == 1);
+                const Image im = make_image(h, g, sx, sy, 0);
+                const int s = a.pstart[rb + wc];
+                walk_culled<true, true>(h, tabrow_s, tabrow, a, g, im, box, sx, sy, 0, s, s + a.count[rb + wc], lst,
+                                        lst_j, direct ? all : none);
+            }
+            if (SPLIT > 1) {
+                store_partial(part, 2 * row + 1, h);
+                h.ax = h.ay = h.az = 0.0f;
+            } else {
+                h.ax += ax0; h.ay += ay0; h.az += az0;
+            }
         }
     }
     return make_float3(h.ax, h.ay, h.az);
@@ -886,6 +1038,9 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                              reinterpret_cast<float4*>(tabB + T * TA + (T * TA & 1)) +
                              (SPLIT > 1 ? kSplitRuns * 3 * kSplitHomes / 4 : 0)) +
                          (threadIdx.x >> 5) * (kListLen * 16u);
+    // ... and of their slots (literal z-wrap walk only), behind all the lists
+    const unsigned lst_j = lst - (threadIdx.x >> 5) * (kListLen * 16u) + (blockDim.x >> 5) * (kListLen * 16u) +
+                           (threadIdx.x >> 5) * (kListLen * 4u);
     for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
         const PairParam pp = a.table[q];
         tab[q] = pp;
@@ -916,7 +1071,11 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     // (~3x the work per particle) and would otherwise sit at the very end of the grid, stretching
     // the kernel's tail.  (Single periodic box only: a slab launches its boundary layers apart.)
     int first_block = 0;
+#ifndef GOF_NO_ROTATE
     if (g.is3d && g.index_wrap_z && a.wrap_mode == kWrapReference && a.home_count2 == 0 && !a.interior_words)
+#else
+    if (false)
+#endif
         first_block = (a.pstart[(g.nlz - 1) * g.nbx * g.nby] - home_begin) / kHomes;
     int blk = (int)blockIdx.x + first_block;
     if (blk >= (int)gridDim.x) blk -= (int)gridDim.x;
@@ -954,16 +1113,24 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     const bool quirk = g.is3d && a.wrap_mode == kWrapReference && (gz == 0 || gz == g.nbz - 1);
 
     const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
-    // Clusters kind: the whole warp walks as one when its home particles share a row of cells and
-    // none is on the literal z-wrap path (all lanes are converged here, padding lanes included:
-    // they repeat the last particle and store nothing).
+    // Clusters kind: the whole warp walks as one when its home particles share a row of cells (all
+    // lanes are converged here, padding lanes included: they repeat the last particle and store
+    // nothing).
     bool as_warp = false;
 #ifndef GOF_NO_WARP_WALK
-    if (KIND == kKindClusters)
-        as_warp = __all_sync(0xffffffffu, !quirk) &&
-                  __reduce_min_sync(0xffffffffu, (unsigned)cyz) == __reduce_max_sync(0xffffffffu, (unsigned)cyz);
+    if (KIND == kKindClusters)  // (one row of cells: one layer, so `quirk` is the same for all lanes)
+        as_warp = __reduce_min_sync(0xffffffffu, (unsigned)cyz) == __reduce_max_sync(0xffffffffu, (unsigned)cyz);
 #endif
-    if (as_warp) {
+    if (as_warp && quirk) {
+        // bottom / top layer in GOF_WRAP_REFERENCE mode: the same walk by the literal rules, out of line
+        const Box box = warp_box(h);
+        const int cx_min = (int)__reduce_min_sync(0xffffffffu, (unsigned)cx);
+        const int cx_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)cx);
+        const float3 f = quirk_walk<SPLIT>(h.x, h.y, h.z, h.type, tabrow_s, tabrow, a, g, box.lox, box.loy, box.loz,
+                                           box.hix, box.hiy, box.hiz, cx, cy, lz, gz, cx_min, cx_max, lst, lst_j,
+                                           share, rows_per_share, part);
+        h.ax = f.x; h.ay = f.y; h.az = f.z;
+    } else if (as_warp) {
         const Box box = warp_box(h);
         const int cx_min = (int)__reduce_min_sync(0xffffffffu, (unsigned)cx);
         const int cx_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)cx);
@@ -991,7 +1158,8 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                     h.ax = h.ay = h.az = 0.0f;
                 }
                 // the cells across the periodic x boundary, for the lanes in the first / last cell of
-                // the row (the shifted image of any other lane is more than a bin away from them)
+                // the row (the shifted image of any other lane is more than a bin away from them; a
+                // lane gets a non-zero sum from at most one of the two)
                 const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
                 h.ax = h.ay = h.az = 0.0f;
                 if (cx_min == 0) {
