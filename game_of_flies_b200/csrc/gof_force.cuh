@@ -1070,15 +1070,46 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     // bottom layer, then the rest: in GOF_WRAP_REFERENCE mode those two layers take the literal path
     // (~3x the work per particle) and would otherwise sit at the very end of the grid, stretching
     // the kernel's tail.  (Single periodic box only: a slab launches its boundary layers apart.)
-    int first_block = 0;
+    // Block -> particles mapping.  In GOF_WRAP_REFERENCE mode the blocks of the top and the bottom z
+    // layer take the literal z-wrap paths and run ~2.5x as long as the others (far more than their
+    // instruction count: a second hot loop on an SM costs instruction-cache misses for everybody).
+    // At the end of the grid they would stretch the kernel's tail (1.12 ms instead of 0.97 at
+    // N = 1M); spread evenly over the launch they slow every SM down (1.23 ms).  They are launched
+    // first, top layer then bottom layer.  (Single periodic box only: a slab launches its boundary
+    // layers apart.)
+    int blk = (int)blockIdx.x;
 #ifndef GOF_NO_ROTATE
-    if (g.is3d && g.index_wrap_z && a.wrap_mode == kWrapReference && a.home_count2 == 0 && !a.interior_words)
-#else
-    if (false)
+    if (g.is3d && g.index_wrap_z && a.wrap_mode == kWrapReference && a.home_count2 == 0 && !a.interior_words) {
+        const int grid = (int)gridDim.x;
+        const int top0 = (a.pstart[(g.nlz - 1) * g.nbx * g.nby] - home_begin) / kHomes;  // first block of the top layer
+        const int n_top = grid - top0;
+        int n_bot = (a.pstart[g.nbx * g.nby] - home_begin + kHomes - 1) / kHomes;        // blocks touching the bottom layer
+        if (n_bot > top0) n_bot = top0;
+        const int nq = n_top + n_bot;  // literal blocks
+        // position r in the order "top layer, bottom layer, the rest" for launch index p
+        const int p = (int)blockIdx.x;
+        int r = p;
+        // The first wave (kWaveSMs x kWaveBlocks launch indices, handed out round-robin over the SMs)
+        // gives the literal blocks to the first W SMs only, so that the two hot loops do not share an SM.
+        constexpr int kWaveSMs = 148, kWaveBlocks = SPLIT == 1 ? GOF_FORCE_MINBLOCKS : 2;
+        const int W = (nq + kWaveBlocks - 1) / kWaveBlocks;
+        if (W <= kWaveSMs && grid >= kWaveSMs * kWaveBlocks) {
+            if (p < kWaveSMs * kWaveBlocks) {
+                const int k = p / kWaveSMs, c = p - k * kWaveSMs;
+                int before = 0;  // literal positions before p
+                for (int kk = 0; kk < k; ++kk) {
+                    const int left = nq - kk * W;
+                    before += left < 0 ? 0 : (left < W ? left : W);
+                }
+                const int left = nq - k * W;
+                const int wk = left < 0 ? 0 : (left < W ? left : W);
+                if (c < wk) r = k * W + c;
+                else r = nq + p - (before + wk);
+            }  // else: every literal block has been placed, r = p
+        }
+        blk = r < n_top ? top0 + r : r - n_top;
+    }
 #endif
-        first_block = (a.pstart[(g.nlz - 1) * g.nbx * g.nby] - home_begin) / kHomes;
-    int blk = (int)blockIdx.x + first_block;
-    if (blk >= (int)gridDim.x) blk -= (int)gridDim.x;
     const int local = blk * kHomes + hl;
     if (a.interior_words && local - hl >= home_count) return;  // whole block past the range
     const bool valid = local < home_count + a.home_count2;
