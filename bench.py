@@ -415,6 +415,10 @@ def main():
     h2d = n * (9 * 4 + 4) + (n * 4 if world > 1 else 0)
     d2h = n * 9 * 4 + (n * 4 if world > 1 else 0)
 
+    if world > 1 and rank == 0 and getattr(runner, "phase_ms", None):
+        pm = runner.phase_ms
+        print(f"[slab timing] per step: prefix (hash, migration, sort) {pm['prefix'] / max(pm['steps'], 1):.4f} ms, "
+              f"forces + halo {pm['forces'] / max(pm['steps'], 1):.4f} ms", file=sys.stderr, flush=True)
     if rank == 0:
         peak, peak_src = measured_peaks()
         force_avg_ms = force_ms / max(force_launches, 1)

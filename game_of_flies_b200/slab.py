@@ -24,6 +24,7 @@ cells, the same order inside a cell (by particle id), the same summation order.
 from __future__ import annotations
 
 import contextlib
+import os
 import ctypes as C
 from dataclasses import dataclass
 
@@ -257,6 +258,10 @@ class LocalComm:
             for w in words:
                 w.fill_(m)
 
+    def allreduce_max_begin(self, words):
+        self.allreduce_max(words)
+        return lambda: None
+
     def exchange(self, transfers):
         for t in transfers:
             for s, d in zip(t.send(), t.recv()):
@@ -310,13 +315,23 @@ class DistComm:
         return {s: vals[s] for s in range(self.world_slabs)}
 
     def allreduce_max(self, words):
+        self.allreduce_max_begin(words)()
+
+    def allreduce_max_begin(self, words):
+        """Start the MAX all-reduce of the slabs' speed words; the returned callable makes the
+        current stream wait for it.  The words are final once the previous step's forces are
+        enqueued, so the reduction can run under this step's hash pass."""
         if len(words) > 1:
             m = torch.stack([w.reshape(()) for w in words]).max()
             for w in words:
                 w.fill_(m)
-        self.dist.all_reduce(words[0], op=self.dist.ReduceOp.MAX)
-        for w in words[1:]:
-            w.copy_(words[0])
+        work = self.dist.all_reduce(words[0], op=self.dist.ReduceOp.MAX, async_op=True)
+
+        def finish():
+            work.wait()
+            for w in words[1:]:
+                w.copy_(words[0])
+        return finish
 
     def exchange(self, transfers):
         """Every rank walks the same global list; NCCL matches the send/recv of a pair of
@@ -346,6 +361,9 @@ class SlabRunner:
         self.world_slabs = int(world_slabs)
         self.comm = comm
         self.messages = 0                 # tensors handed to the transport so far (diagnostics)
+        # GOF_SLAB_TIMING=1: device time of the serial part of a step (hash + migration + sort) and
+        # of the forces (with the halo traffic underneath), summed over the steps, in `phase_ms`
+        self.phase_ms = {"prefix": 0.0, "forces": 0.0, "steps": 0} if os.environ.get("GOF_SLAB_TIMING") else None
 
     def _below(self, s):
         return (s - 1) % self.world_slabs
@@ -356,6 +374,16 @@ class SlabRunner:
     def step(self, n_steps: int = 1, timestep=None):
         W = self.world_slabs
         for _ in range(n_steps):
+            marks = None
+            if self.phase_ms is not None:
+                e0 = next(iter(self.slabs.values()))
+                ms = torch.cuda.current_stream(e0.index)
+                marks = [ms.record_event(torch.cuda.Event(enable_timing=True))]
+            # ---- 0. the global maximum speed of the state as it stands (adaptive timestep): the
+            # reduction runs on the transport's stream under the hash pass
+            finish_speed = None
+            if timestep is None:
+                finish_speed = self.comm.allreduce_max_begin([e.speed_word() for e in self.slabs.values()])
             # ---- 1. bin, pack leavers; the fixed-size migration buffers go to the neighbours ---
             for e in self.slabs.values():
                 e.phase_hash()
@@ -369,11 +397,13 @@ class SlabRunner:
                                           send=lambda s=s: [self.slabs[s].mig_send(1)],
                                           recv=lambda s=s: [self.slabs[self._above(s)].mig_recv(0)]))
             self.comm.exchange(transfers)
-            if timestep is None:
-                self.comm.allreduce_max([e.speed_word() for e in self.slabs.values()])
+            if finish_speed is not None:
+                finish_speed()
             # ---- 2. append arrivals (counts are read on the device), sort ---------------------
             for e in self.slabs.values():
                 e.phase_sort(timestep)
+            if marks is not None:
+                marks.append(ms.record_event(torch.cuda.Event(enable_timing=True)))
             # ---- 3a. interior forces start now; sizes + halo layers move underneath ------------
             overlap = self.overlap and all(hasattr(e, "side_stream") for e in self.slabs.values())
             if overlap:
@@ -421,6 +451,12 @@ class SlabRunner:
                 for s in self.slabs:
                     main[s].wait_event(done_ev)
             self.messages += 4 * W
+            if marks is not None:
+                marks.append(ms.record_event(torch.cuda.Event(enable_timing=True)))
+                marks[2].synchronize()
+                self.phase_ms["prefix"] += marks[0].elapsed_time(marks[1])
+                self.phase_ms["forces"] += marks[1].elapsed_time(marks[2])
+                self.phase_ms["steps"] += 1
 
     def gather_state(self, num_particles: int):
         """This process's particles scattered into (3, N) arrays by id (others stay NaN)."""
