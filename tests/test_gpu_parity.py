@@ -286,6 +286,25 @@ def test_graph_launched_steps_equal_kernel_launched_steps(gof, kinds, counts, li
     assert outs[0]["dt"] == outs[1]["dt"]
 
 
+@pytest.mark.parametrize("wrap_mode", [orc.WRAP_REFERENCE, orc.WRAP_MINIMAGE], ids=["refwrap", "minimage"])
+def test_clustered_state_parity(gof, wrap_mode):
+    """Parity on an EVOLVED Clusters state: after 150 steps the particles have clumped (cells with
+    twice the mean population and more, long candidate runs, many chunks per run in the culled
+    whole-warp walk); one more step from that state must agree with the oracle like any other."""
+    st = random_state([5000] * 4, (105, 95, 110), seed=17, kinds="clusters", speed=1.0)
+    e = engine_from_state(gof, st, wrap_mode)
+    e.step(150)
+    out = e.download(pos=True, vel=True, acc=True)
+    _, cnt, _, _ = e.read_bins()
+    e.close()
+    assert cnt.max() > 2 * cnt.mean(), "the run should have clumped"
+    evolved = dict(st)
+    for k in ("pos", "vel", "acc"):
+        evolved[k] = out[k].astype(np.float64)
+    check_engine_step(gof, evolved, None, wrap_mode=wrap_mode)
+    check_accelerator(gof, evolved, wrap_mode)
+
+
 def test_engine_is_deterministic_and_keeps_every_particle(gof):
     st = random_state([30000] * 5, (220, 220, 220), seed=5, kinds="clusters", speed=1.0)
     outs = []
