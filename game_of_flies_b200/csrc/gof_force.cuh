@@ -492,17 +492,28 @@ __device__ __forceinline__ void repair_quirk(float3& rep, const Home& h, const P
 // does not depend on which walk its warp takes.
 struct Box { float lox, loy, loz, hix, hiy, hiz; };
 
+// order-preserving map of a float onto unsigned (any sign: a caller may upload positions that
+// are outside the box, the boundary condition only brings them back after the step)
+__device__ __forceinline__ unsigned float_key(float v)
+{
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 __device__ __forceinline__ Box warp_box(const Home& h)
 {
-    // coordinates are >= 0: their bit patterns order like the values
-    const unsigned ux = __float_as_uint(fabsf(h.x)), uy = __float_as_uint(fabsf(h.y)), uz = __float_as_uint(fabsf(h.z));
+    const unsigned ux = float_key(h.x), uy = float_key(h.y), uz = float_key(h.z);
     Box b;
-    b.lox = __uint_as_float(__reduce_min_sync(0xffffffffu, ux));
-    b.loy = __uint_as_float(__reduce_min_sync(0xffffffffu, uy));
-    b.loz = __uint_as_float(__reduce_min_sync(0xffffffffu, uz));
-    b.hix = __uint_as_float(__reduce_max_sync(0xffffffffu, ux));
-    b.hiy = __uint_as_float(__reduce_max_sync(0xffffffffu, uy));
-    b.hiz = __uint_as_float(__reduce_max_sync(0xffffffffu, uz));
+    b.lox = key_float(__reduce_min_sync(0xffffffffu, ux));
+    b.loy = key_float(__reduce_min_sync(0xffffffffu, uy));
+    b.loz = key_float(__reduce_min_sync(0xffffffffu, uz));
+    b.hix = key_float(__reduce_max_sync(0xffffffffu, ux));
+    b.hiy = key_float(__reduce_max_sync(0xffffffffu, uy));
+    b.hiz = key_float(__reduce_max_sync(0xffffffffu, uz));
     return b;
 }
 
