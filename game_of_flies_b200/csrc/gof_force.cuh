@@ -1019,7 +1019,7 @@ __device__ __noinline__ float3 quirk_walk(float hx, float hy, float hz, int type
 // in shared memory; warp 0 then folds the 18 partials in the order the one-thread kernel adds
 // them, so the result is bit-identical to SPLIT == 1 whatever the split.
 #ifndef GOF_FORCE_MINBLOCKS
-#define GOF_FORCE_MINBLOCKS 5
+#define GOF_FORCE_MINBLOCKS 4
 #endif
 template <int KIND, int MODE, int SPLIT>
 #ifndef GOF_BOIDS_MINBLOCKS
