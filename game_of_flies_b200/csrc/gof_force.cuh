@@ -1022,11 +1022,15 @@ __device__ __noinline__ float3 quirk_walk(float hx, float hy, float hz, int type
 #define GOF_FORCE_MINBLOCKS 4
 #endif
 template <int KIND, int MODE, int SPLIT>
+#ifndef GOF_MIXED_MINBLOCKS
+#define GOF_MIXED_MINBLOCKS 5
+#endif
 #ifndef GOF_BOIDS_MINBLOCKS
 #define GOF_BOIDS_MINBLOCKS 6
 #endif
 __global__ void __launch_bounds__(SPLIT == 1 ? kForceThreads : kSplitHomes * SPLIT,
-                                  SPLIT == 1 ? (KIND == kKindBoids ? GOF_BOIDS_MINBLOCKS : GOF_FORCE_MINBLOCKS)
+                                  SPLIT == 1 ? (KIND == kKindBoids ? GOF_BOIDS_MINBLOCKS
+                                                : (KIND == kKindMixed ? GOF_MIXED_MINBLOCKS : GOF_FORCE_MINBLOCKS))
                                              : (SPLIT == 3 ? 6 : 2))
 k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
 {
