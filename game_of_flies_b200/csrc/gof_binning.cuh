@@ -295,10 +295,18 @@ k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict
     const float4 p = posw_in[i];
     int rank = 0;
     if (slot_key) {
+        // branch-free, four entries in flight (the short-circuit form stalled on its branches)
         const unsigned key = __float_as_uint(fabsf(p.x));
-        for (int t = b; t < e; ++t) {
+        int t = b;
+        for (; t + 4 <= e; t += 4) {
+            const unsigned k0 = slot_key[t], k1 = slot_key[t + 1], k2 = slot_key[t + 2], k3 = slot_key[t + 3];
+            const int i0 = slot_id[t], i1 = slot_id[t + 1], i2 = slot_id[t + 2], i3 = slot_id[t + 3];
+            rank += (int)((k0 < key) | ((k0 == key) & (i0 < id))) + (int)((k1 < key) | ((k1 == key) & (i1 < id))) +
+                    (int)((k2 < key) | ((k2 == key) & (i2 < id))) + (int)((k3 < key) | ((k3 == key) & (i3 < id)));
+        }
+        for (; t < e; ++t) {
             const unsigned kt = slot_key[t];
-            rank += (kt < key) || (kt == key && slot_id[t] < id);
+            rank += (int)((kt < key) | ((kt == key) & (slot_id[t] < id)));
         }
     } else {
         for (int t = b; t < e; ++t) rank += (slot_id[t] < id);
