@@ -1156,7 +1156,28 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     // PER LANE (a warp that straddles the layer boundary runs both paths one after the other):
     // what a particle computes must not depend on its warp-mates, or the result would change
     // with the decomposition.  The votes inside the fast path use the active mask.
-    const bool quirk = g.is3d && a.wrap_mode == kWrapReference && (gz == 0 || gz == g.nbz - 1);
+    //
+    // Which home cells really need it.  With the home particle or the neighbour as the reference's
+    // thread i, the literal rules (acceleration_updater.py:325-328) come to this for nbz >= 4: a pair
+    // ACROSS the periodic z boundary interacts only if its upper particle has y > Lz - r_max (the
+    // `pos_y[i]` of the quirk), and a pair on one side of it is lost if the upper-role particle has
+    // such a y and the other one z < r_max.  Away from that band of y nothing else is left of the
+    // rules than "no interaction across the z boundary".  So only the home cells whose own row of
+    // cells, or one of the two next to it in y, reaches into the band take the literal paths; the
+    // other cells of the bottom / top layer walk like interior cells and skip the three stencil rows
+    // across the boundary (`skip_dz`).  The choice depends on the home cell alone.
+    bool quirk = g.is3d && a.wrap_mode == kWrapReference && (gz == 0 || gz == g.nbz - 1);
+    int skip_dz = 2;  // stencil dz to leave out (2: none)
+    if (quirk && g.nbz >= 4) {
+        const double band = g.Lzd - g.rmaxd - 1e-6 * g.Lzd;  // (a little below the threshold of the test)
+        const int rm = cy > 0 ? cy - 1 : g.nby - 1, rp = cy < g.nby - 1 ? cy + 1 : 0;
+        const bool in_band = (double)(cy + 1) * g.bsy > band || (double)(rm + 1) * g.bsy > band ||
+                             (double)(rp + 1) * g.bsy > band;
+        if (!in_band) {
+            quirk = false;
+            skip_dz = gz == 0 ? -1 : 1;
+        }
+    }
 
     const int dz_lo = g.is3d ? -1 : 0, dz_hi = g.is3d ? 1 : 0;
     // Clusters kind: the whole warp walks as one when its home particles share a row of cells (all
@@ -1190,6 +1211,13 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
             }
             for (int dyi = -1; dyi <= 1; ++dyi, ++row) {
                 if (SPLIT > 1 && row / rows_per_share != share) continue;
+                if (dzi == skip_dz) {  // across the z boundary, reference wrap: no interaction
+                    if (SPLIT > 1) {
+                        store_partial(part, 2 * row, h);
+                        store_partial(part, 2 * row + 1, h);
+                    }
+                    continue;
+                }
                 int ny = cy + dyi, sy = 0;
                 if (ny < 0) { ny += g.nby; sy = 1; }
                 else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
@@ -1235,6 +1263,13 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
             }
             for (int dyi = -1; dyi <= 1; ++dyi, ++row) {
                 if (SPLIT > 1 && row / rows_per_share != share) continue;
+                if (dzi == skip_dz) {  // across the z boundary, reference wrap: no interaction
+                    if (SPLIT > 1) {
+                        store_partial(part, 2 * row, h);
+                        store_partial(part, 2 * row + 1, h);
+                    }
+                    continue;
+                }
                 int ny = cy + dyi, sy = 0;
                 if (ny < 0) { ny += g.nby; sy = 1; }
                 else if (ny >= g.nby) { ny -= g.nby; sy = -1; }

@@ -155,6 +155,11 @@ def test_accelerator_on_golden_states(gof, path, wrap_mode):
     ("boids", [3000] * 2, (90, 90, 0), 12.0),
     ("mixed", [2500] * 6, (110, 110, 110), 8.0),
     ("mixed", [1200] * 8, (100, 100, 100), 8.0),
+    # Ly > Lz: the band y > Lz - r_max of the reference's z-wrap quirk covers half of the y range
+    ("clusters", [4000] * 5, (100, 160, 90), 3.0),
+    ("mixed", [2500] * 6, (90, 150, 100), 8.0),
+    # Ly < Lz - r_max: no particle is in the band
+    ("clusters", [4000] * 4, (120, 80, 130), 3.0),
 ])
 def test_accelerator_random_states(gof, kinds, counts, limits, speed, wrap_mode):
     st = random_state(counts, limits, seed=11, kinds=kinds, speed=speed)
@@ -216,6 +221,7 @@ def test_engine_step_on_golden_states(gof, path):
     ("clusters", [5000] * 3, (270, 270, 0), 2.0, 0.02),
     ("boids", [20000] * 3, (160, 160, 160), 9.0, None),
     ("mixed", [8000] * 8, (165, 165, 165), 6.0, None),
+    ("clusters", [12000] * 5, (150, 230, 140), 2.0, None),   # the quirk's y band spans many rows of cells
 ])
 def test_engine_step_random_states(gof, kinds, counts, limits, speed, ts):
     st = random_state(counts, limits, seed=23, kinds=kinds, speed=speed)
