@@ -1023,7 +1023,7 @@ __device__ __noinline__ float3 quirk_walk(float hx, float hy, float hz, int type
 #endif
 template <int KIND, int MODE, int SPLIT>
 #ifndef GOF_MIXED_MINBLOCKS
-#define GOF_MIXED_MINBLOCKS 5
+#define GOF_MIXED_MINBLOCKS 6
 #endif
 #ifndef GOF_BOIDS_MINBLOCKS
 #define GOF_BOIDS_MINBLOCKS 6
