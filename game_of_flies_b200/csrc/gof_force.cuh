@@ -8,12 +8,19 @@
 // The reference walks HALF the stencil (5 / 14 bins) and pushes the reaction
 // onto the neighbour with atomics.  Here every particle GATHERS over the full
 // 9 / 27 cell stencil: no atomics on the accelerations, a fixed summation
-// order (rows in (dz, dy) order, cells by x, particles by id) and therefore
+// order (rows in (dz, dy) order, cells by x, particles by (x, id)) and therefore
 // bit-reproducible results.  Because the particles are sorted by cell, the
 // three x-adjacent cells of a stencil row are ONE contiguous run of the float4
-// position array; consecutive threads are consecutive particles of the same
-// cell, so all lanes of a warp read the same neighbour at the same time (one
-// 16-byte broadcast load served by L1).
+// position array.  How a warp goes through the runs depends on the kind of system:
+//   Clusters kind  the 32 home particles of a warp walk the union of their runs as one,
+//                  candidates culled against the box of the 32 (walk_culled); warps that
+//                  straddle two rows of cells fall back to one walk per lane (run_pairs)
+//   Boids kind     per lane; pairs in range are queued and the interactions done with every
+//                  lane on its own entries (pair_note / queue_drain)
+//   mixed          per lane, interaction behind a branch (pair_branchy)
+// plus the literal paths of the reference's z-wrap quirk (quirk_walk, quirk_home) for the few
+// home cells that need them, and the split variant for small systems (SPLIT > 1).
+// A particle's result never depends on which of these paths its warp takes.
 #pragma once
 #include <climits>
 #include "gof_binning.cuh"
@@ -670,11 +677,7 @@ __device__ __forceinline__ void run_image(Home& h, RowAddr tabrow_s,
                                           const Geometry& g, int sx, int sy, int sz, int s, int e, BoidQueue& q)
 {
     const Image im = make_image(h, g, sx, sy, sz);
-#ifdef GOF_LOWFIX_ALWAYS
-    if (true)
-#else
     if (__any_sync(__activemask(), im.up && e > s))
-#endif
         run_pairs<KIND, true>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e, q);
     else
         run_pairs<KIND, false>(h, tabrow_s, tabrow, boid_acc, a, g, im, s, e, q);
