@@ -493,7 +493,7 @@ __device__ __forceinline__ void repair_quirk(float3& rep, const Home& h, const P
 // lane meets a superset of its own candidates in the same order, and the extra ones are farther
 // than one bin (>= r_max) from it, i.e. add exactly zero.  What this buys is warp-uniform control
 // flow, which makes culling possible: about half of the candidates are out of range for EVERY
-// lane.  Per chunk of 32 candidates each lane tests ONE against the box of the warp's home
+// lane.  Per chunk of 64 candidates each lane tests TWO against the box of the warp's home
 // particles, the votes are collected with a ballot, and only the surviving candidates are
 // evaluated, four at a time as in the per-lane walk.  A skipped candidate would have added exactly zero, so a particle's result
 // does not depend on which walk its warp takes.
@@ -524,7 +524,7 @@ __device__ __forceinline__ Box warp_box(const Home& h)
     return b;
 }
 
-constexpr int kListLen = 64;  // survivors a warp can hold: fewer than 4 left over + 32 of a chunk
+constexpr int kListLen = 128;  // survivors a warp can hold (a power of two): fewer than 4 left over + 64 of a chunk
 
 __device__ __forceinline__ void sts4(unsigned saddr, const float4 v)
 {
@@ -586,7 +586,7 @@ __device__ __forceinline__ void walk_group(Home& h, float3& rep, RowAddr tabrow_
 }
 
 // `lst`: shared-memory address of the warp's survivor list (kListLen float4, a ring).  Per chunk
-// of 32 candidates every lane loads one and tests it against the box; the survivors are appended
+// of 64 candidates every lane loads two and tests them against the box; the survivors are appended
 // in order (ballot + prefix count), and the list is consumed four at a time, left-overs carried
 // to the next chunk.  The run's last group is padded with a particle parked far outside the box.
 //
@@ -609,12 +609,14 @@ __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const Pai
     const float loz = b.loz + tz - g.cull_slack, hiz = b.hiz + tz + g.cull_slack;
     const unsigned lane = (unsigned)lane_id(), below = (1u << lane) - 1u;
     unsigned head = 0u, len = 0u;  // warp-uniform; head stays a multiple of four
-    for (int base = s; base < e; base += 32) {
-        const int jl = base + (int)lane;
-        bool keep = false;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (jl < e) {
-            p = ldg4(a.posw + jl);
+    // chunks of 64 candidates, two per lane: half as many ballot / append / syncwarp rounds
+    for (int base = s; base < e; base += 64) {
+        const int j0 = base + (int)lane, j1 = j0 + 32;
+        bool keep0 = false, keep1 = false;
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (j0 < e) p0 = ldg4(a.posw + j0);
+        if (j1 < e) p1 = ldg4(a.posw + j1);
+        auto reach = [&](const float4 p) {
             const float ex = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
             const float ey = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
             float ez = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
@@ -623,15 +625,22 @@ __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const Pai
                 const float dn = fmaxf(fmaxf((loz - g.Lz) - p.z, p.z - (hiz - g.Lz)), 0.0f);
                 ez = fminf(ez, fminf(up, dn));
             }
-            keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < g.cull_r2;
+            return fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < g.cull_r2;
+        };
+        if (j0 < e) keep0 = reach(p0);
+        if (j1 < e) keep1 = reach(p1);
+        const unsigned m0 = __ballot_sync(0xffffffffu, keep0), m1 = __ballot_sync(0xffffffffu, keep1);
+        if (keep0) {
+            const unsigned at = (head + len + __popc(m0 & below)) & (kListLen - 1);
+            sts4(lst + (at << 4), p0);
+            if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (at << 2)), "r"(j0) : "memory");
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const unsigned at = (head + len + __popc(m & below)) & (kListLen - 1);
-            sts4(lst + (at << 4), p);
-            if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (at << 2)), "r"(jl) : "memory");
+        if (keep1) {
+            const unsigned at = (head + len + __popc(m0) + __popc(m1 & below)) & (kListLen - 1);
+            sts4(lst + (at << 4), p1);
+            if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (at << 2)), "r"(j1) : "memory");
         }
-        len += __popc(m);
+        len += __popc(m0) + __popc(m1);
         __syncwarp();
         while (len >= 4u) {
             const unsigned at = head & (kListLen - 1);
