@@ -230,7 +230,8 @@ def workload_config(args, hs, n_total, note=None):
     cfg = {
         "workload": f"{kind.capitalize()} {dims}D, {species} species, N={n_total}, periodic box "
                     f"{tuple(round(float(x), 2) for x in hs['box'])}, density {hs['density']:.4g}, "
-                    f"r_max {float(hs['r_max']):.3f}, uniform random start, adaptive timestep",
+                    f"r_max {float(hs['r_max']):.3f}, uniform random start, "
+                    + ("adaptive timestep" if args.timestep is None else f"fixed timestep {args.timestep}"),
         "particles_per_gpu": int(n_total // max(int(os.environ.get("WORLD_SIZE", "1")), 1)),
         "bins": [int(hs["num_bin_x"]), int(hs["num_bin_y"]), int(hs["num_bin_z"])],
         "wrap_mode": getattr(args, "wrap", "reference"),
@@ -261,6 +262,8 @@ def main():
                     help="periodic wrap semantics: the reference's (z-wrap quirk included) or minimum image")
     ap.add_argument("--packed", action="store_true", help="use the packed two-homes-per-lane Clusters kernel")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--timestep", type=float, default=None,
+                    help="fixed timestep (default: the reference's adaptive one, 0.4 / max speed)")
     ap.add_argument("--force-split", type=int, default=-1, choices=(-1, 1, 3, 9),
                     help="warps per home particle in the small-system force kernel (-1: automatic)")
     args = ap.parse_args()
@@ -311,12 +314,12 @@ def main():
         eng = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), device=device,
                              packed=args.packed, wrap_mode=wrap_mode)
         eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
-        step = lambda k: eng.step(k)
+        step = lambda k: eng.step(k, args.timestep)
 
         def e2e_step():
             nonlocal h_pos, h_vel, h_acc, o_pos, o_vel, o_acc
             eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
-            eng.step(1)
+            eng.step(1, args.timestep)
             eng.download_into(pos=o_pos, vel=o_vel, acc=o_acc)
             torch.cuda.current_stream(device).synchronize()
             # the next step of a host-driven loop starts from what came back
@@ -353,12 +356,12 @@ def main():
                          device=device, wrap_mode=wrap_mode)
         eng.upload(pos, types, ids, vel=zeros, acc=zeros)
         runner = SlabRunner({rank: eng}, world, DistComm(world, device=device))
-        step = lambda k: runner.step(k)
+        step = lambda k: runner.step(k, args.timestep)
         state = {"pos": pos, "vel": zeros, "acc": zeros, "types": types, "ids": ids}
 
         def e2e_step():
             eng.upload(state["pos"], state["types"], state["ids"], vel=state["vel"], acc=state["acc"])
-            runner.step(1)
+            runner.step(1, args.timestep)
             d = eng.download()
             state["pos"], state["vel"], state["acc"], state["ids"] = d["pos"], d["vel"], d["acc"], d["ids"]
             # types travel with the particles: recover them from the ids (species are id ranges per rank)
