@@ -87,3 +87,22 @@ def test_compute_entry_points_fail_loudly_without_gpu():
     from game_of_flies_b200.simulation import Simulation
     with pytest.raises(RuntimeError):
         Simulation(np.array([50, 50]), np.array([0]), seed=1, limits=(100, 100, 0))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs the oracle port on the host cores (no GPU involved) and
+    prints one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--reference-particles", "4000"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "particle-updates/sec"
+    assert line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"]
