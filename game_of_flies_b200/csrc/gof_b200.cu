@@ -293,15 +293,29 @@ static size_t force_smem_bytes(int T, int kind, int split)
            (kind == kKindClusters ? (size_t)(split > 1 ? split : kForceThreads / 32) * kListLen * (sizeof(float4) + sizeof(int)) : 0);
 }
 
+// cudaFuncSetAttribute is per device: remember per kernel instantiation which devices have it
+// (a process may drive engines on several GPUs, from several threads).
+static bool attr_needed(std::atomic<unsigned long long>& done)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    return !((done.load(std::memory_order_relaxed) >> dev) & 1ull);
+}
+static void attr_done(std::atomic<unsigned long long>& done)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_relaxed);
+}
+
 template <int KIND, int MODE, int SPLIT>
 static int launch_force_t(const Geometry& g, const ForceArgs& a, cudaStream_t st)
 {
     const size_t smem = force_smem_bytes(a.T, KIND, SPLIT);
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};  // per instantiation, one bit per device
+    if (attr_needed(attr_set)) {
         GOF_CUDA(cudaFuncSetAttribute(k_force<KIND, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       100 * 1024));
-        attr_set = true;
+        attr_done(attr_set);
     }
     const int homes = SPLIT == 1 ? kForceThreads : kSplitHomes;
     GOF_LAUNCH((k_force<KIND, MODE, SPLIT>), cdiv(a.home_count + a.home_count2, homes), homes * SPLIT, smem, st, g, a);
@@ -389,10 +403,10 @@ static size_t force2_smem_bytes(int T)
 static int launch_force2(const Geometry& g, const ForceArgs& a, int slots, cudaStream_t st)
 {
     if (slots <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (attr_needed(attr_set)) {
         GOF_CUDA(cudaFuncSetAttribute(k_force2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
+        attr_done(attr_set);
     }
     GOF_LAUNCH(k_force2, cdiv(cdiv(slots, 2), kForce2Threads), kForce2Threads, force2_smem_bytes(a.T), st, g, a);
     return 0;
