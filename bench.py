@@ -139,8 +139,8 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def recorded_traffic(workload: str, n: int):
-    """dram bytes per force-kernel launch from the committed ncu capture, if one matches."""
+def recorded_capture(workload: str, n: int):
+    """The committed ncu capture of the force kernel that matches this workload, if any."""
     path = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
     if not os.path.exists(path):
         return None
@@ -149,10 +149,16 @@ def recorded_traffic(workload: str, n: int):
             rec = json.load(f)
         for r in rec.get("captures", []):
             if r.get("workload") == workload and int(r.get("particles", -1)) == n:
-                return float(r["dram_bytes_per_launch"])
+                return r
     except Exception:
         return None
     return None
+
+
+def recorded_traffic(workload: str, n: int):
+    """dram bytes per force-kernel launch from the committed ncu capture, if one matches."""
+    r = recorded_capture(workload, n)
+    return float(r["dram_bytes_per_launch"]) if r else None
 
 
 def oracle_sim_from(hs, n_threads):
@@ -433,6 +439,9 @@ def main():
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_src,
             "traffic": recorded_traffic(args.workload, n),
+            # the kernel's real limit, from the same ncu capture (profiles/): issue slots in use
+            "issue_active_pct": (recorded_capture(args.workload, n) or {}).get("issue_active_pct"),
+            "active_lanes": (recorded_capture(args.workload, n) or {}).get("active_lanes_per_instruction"),
             "algorithmic_bytes_per_launch": FORCE_BYTES_PER_PARTICLE * n,
             "avg_launch_ms": force_avg_ms, "launches_timed": force_launches,
             "share_of_step": force_ms / ms_total if ms_total > 0 else None,
