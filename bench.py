@@ -266,7 +266,6 @@ def main():
                     help="do not overwrite a 256 MiB buffer between timed steps")
     ap.add_argument("--wrap", default="reference", choices=["reference", "minimage"],
                     help="periodic wrap semantics: the reference's (z-wrap quirk included) or minimum image")
-    ap.add_argument("--packed", action="store_true", help="use the packed two-homes-per-lane Clusters kernel")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--timestep", type=float, default=None,
                     help="fixed timestep (default: the reference's adaptive one, 0.4 / max speed)")
@@ -318,7 +317,7 @@ def main():
         o_vel = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
         o_acc = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
         eng = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), device=device,
-                             packed=args.packed, wrap_mode=wrap_mode)
+                             wrap_mode=wrap_mode)
         eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
         step = lambda k: eng.step(k, args.timestep)
 

@@ -16,7 +16,6 @@ GOF_ABI_VERSION = 1
 WRAP_REFERENCE = 0
 WRAP_MINIMAGE = 1
 MAX_TYPES = 16
-KERNEL_SCALAR, KERNEL_PACKED = 0, 1
 
 E_INVALID, E_STATE, E_NOMEM, E_GRID = -1, -2, -3, -4
 
@@ -73,7 +72,6 @@ SIGNATURES = {
     "gof_engine_snapshot_stage": (_i, [_vp, _vp]),
     "gof_engine_snapshot_copy": (_i, [_vp, _vp, _vp]),
     "gof_engine_read_bins": (_i, [_vp] + [_vp] * 4 + [_vp]),
-    "gof_engine_set_kernel": (_i, [_vp, _i]),
     "gof_set_force_split": (_i, [_i]),
     "gof_engine_set_graph": (_i, [_vp, _i]),
     "gof_engine_timing": (_i, [_vp, _i]),
@@ -110,12 +108,17 @@ def load() -> C.CDLL:
     if path == _build.LIB and _build.stale():
         try:
             _build.build()
-        except Exception as exc:  # no nvcc on this host
+        except FileNotFoundError as exc:  # no nvcc on this host
             if not os.path.exists(path):
                 raise ImportError(
                     f"{path} is missing and could not be built ({exc}). Run "
                     "`python game_of_flies_b200/build.py` where nvcc is available; "
                     "this package has no CPU fallback.") from exc
+            import warnings
+            warnings.warn(f"{path} is OLDER than its sources and nvcc is not available to rebuild it: "
+                          "loading the stale library", RuntimeWarning, stacklevel=2)
+        except Exception as exc:  # nvcc is here and the sources do not compile: never run old kernels silently
+            raise ImportError(f"{path} is stale and rebuilding it failed: {exc}") from exc
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch

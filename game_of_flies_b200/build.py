@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgof_b200.so")
 SOURCES = [os.path.join(CSRC, "gof_b200.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("gof_kernels.cuh", "gof_binning.cuh", "gof_force.cuh")]
+import glob  # noqa: E402
+
+HEADERS = sorted(glob.glob(os.path.join(CSRC, "*.cuh")))  # every header gof_b200.cu can include
 HEADERS.append(os.path.join(os.path.dirname(HERE), "include", "gof_b200.h"))
 
 def nvcc_path() -> str:

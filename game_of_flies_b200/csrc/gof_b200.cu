@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../include/gof_b200.h"
-#include "gof_force2.cuh"
+#include "gof_force.cuh"
 
 using namespace gof;
 
@@ -377,38 +377,17 @@ static int launch_force(const Geometry& g, const ForceArgs& a, int kind, int mod
     return launch_force_m<kModeScatter>(g, a, kind, st);
 }
 
-// exclusive scan of m ints (PAD2: of the counts rounded up to even); tile_sums needs
-// cdiv(m, kScanTile) ints
-template <bool PAD2>
+// exclusive scan of m ints; tile_sums needs cdiv(m, kScanTile) ints
 static int launch_scan(const int* in, int m, int* tile_sums, int* out, cudaStream_t st)
 {
     const int tiles = cdiv(m, kScanTile);
     if (tiles <= 1) {
-        GOF_LAUNCH(k_scan_apply<PAD2>, 1, kScanThreads, 0, st, in, m, (const int*)nullptr, out);
+        GOF_LAUNCH(k_scan_apply, 1, kScanThreads, 0, st, in, m, (const int*)nullptr, out);
         return 0;
     }
-    GOF_LAUNCH(k_scan_tile_sums<PAD2>, tiles, kScanThreads, 0, st, in, m, tile_sums);
+    GOF_LAUNCH(k_scan_tile_sums, tiles, kScanThreads, 0, st, in, m, tile_sums);
     GOF_LAUNCH(k_scan_tile_prefix, 1, kScanThreads, 0, st, tile_sums, tiles);
-    GOF_LAUNCH(k_scan_apply<PAD2>, tiles, kScanThreads, 0, st, in, m, (const int*)tile_sums, out);
-    return 0;
-}
-
-static size_t force2_smem_bytes(int T)
-{
-    return (size_t)T * T * sizeof(PairParam) + (size_t)T * T * T * (2 * sizeof(float4) + sizeof(float2)) +
-           (size_t)T * (T | 1) * (sizeof(float4) + sizeof(float2)) + 32;
-}
-
-// the packed two-homes-per-lane Clusters kernel; `slots` = upper bound of padded slots
-static int launch_force2(const Geometry& g, const ForceArgs& a, int slots, cudaStream_t st)
-{
-    if (slots <= 0) return 0;
-    static std::atomic<unsigned long long> attr_set{0};
-    if (attr_needed(attr_set)) {
-        GOF_CUDA(cudaFuncSetAttribute(k_force2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_done(attr_set);
-    }
-    GOF_LAUNCH(k_force2, cdiv(cdiv(slots, 2), kForce2Threads), kForce2Threads, force2_smem_bytes(a.T), st, g, a);
+    GOF_LAUNCH(k_scan_apply, tiles, kScanThreads, 0, st, in, m, (const int*)tile_sums, out);
     return 0;
 }
 
@@ -538,7 +517,7 @@ k_snapshot(const float4* __restrict__ posw, const float4* __restrict__ veli, int
     xyz[3 * (size_t)id + 2] = p.z;
 }
 
-// bins of the last step in the reference's layout; the snapshot may sit on padded segments
+// bins of the last step in the reference's layout
 __global__ void __launch_bounds__(kEwThreads)
 k_export_bins(const float4* __restrict__ veli_sorted, const int* __restrict__ cell_sorted,
               const int* __restrict__ start, const int* __restrict__ pstart,
@@ -549,7 +528,7 @@ k_export_bins(const float4* __restrict__ veli_sorted, const int* __restrict__ ce
     if (k >= pstart[num_cells]) return;
     const int c = cell_sorted[k];
     const int r = k - pstart[c];
-    if (r >= count[c]) return;  // padding slot
+    if (r >= count[c]) return;
     const int id = __float_as_int(veli_sorted[k].w);
     if (particle_bins) particle_bins[id] = c;
     if (particle_indices) {
@@ -636,7 +615,7 @@ extern "C" int gof_setup_bins(const float* d_pos_x, const float* d_pos_y, const 
                    (const float4*)nullptr, (const float4*)nullptr, d_pos_x, d_pos_y, d_pos_z, n, (const int*)nullptr, g,
                    d_particle_bins, d_bin_offsets, d_counts, none);
     }
-    if (int rc = launch_scan<false>(d_counts, num_bins, tile_sums, d_starts, st)) return rc;
+    if (int rc = launch_scan(d_counts, num_bins, tile_sums, d_starts, st)) return rc;
     if (n > 0) {
         GOF_LAUNCH(k_scatter_ids<true>, cdiv(n, kBinThreads), kBinThreads, 0, st, (const float4*)nullptr, n,
                    (const int*)nullptr, d_particle_bins, d_bin_offsets, d_starts, slot_id, (const float4*)nullptr,
@@ -782,8 +761,7 @@ struct gof_engine {
     Geometry geom{};
     HostSpecies species;
     bool species_dirty = true;
-    bool bound = false, uploaded = false, binned = false, binned_packed = false;
-    bool want_packed = false;  // gof_engine_set_kernel
+    bool bound = false, uploaded = false, binned = false;
     int parity = 0;  // which max_sq_speed slot describes the resident velocities
 
     // carved from the arena
@@ -791,8 +769,8 @@ struct gof_engine {
     float4 *posw[2] = {nullptr, nullptr}, *veli[2] = {nullptr, nullptr}, *acc = nullptr;
     int *cell_of = nullptr, *off = nullptr, *slot_id = nullptr, *cell_sorted = nullptr;
     unsigned* slot_key = nullptr;  // sort key inside a cell (bits of x), parallel to slot_id
-    int *count = nullptr, *start = nullptr, *pstart = nullptr, *tile_sums = nullptr;
-    int slot_capacity = 0;                      // capacity + num_cells + 2 (even-padded segments)
+    int *count = nullptr, *start = nullptr, *tile_sums = nullptr;
+    int slot_capacity = 0;                      // capacity (+ the two halo layers in slab mode)
     StepScalars* scalars = nullptr;
     DeviceSpecies dspecies{};
     float* stage[9] = {};  // SoA staging: pos xyz, vel xyz, acc xyz
@@ -818,7 +796,6 @@ struct gof_engine {
         cudaGraphExec_t exec = nullptr;
         float timestep = 0.f;
         int wrap_mode = 0, split = 0, generation = -1, launches = 0;
-        bool packed = false;
     } graphs[2];
     bool use_graph = true;
     int generation = 0;             // bumped by whatever invalidates captured graphs
@@ -843,10 +820,10 @@ static size_t engine_layout(gof_engine* e, char* base)
     };
     const size_t cap = (size_t)e->capacity;
     const size_t cells = (size_t)e->geom.num_cells + 2;
-    // padded snapshot: at most one extra slot per cell; slab mode appends the two halo layers
-    const size_t slots = cap + cells + 2 * (size_t)e->halo_capacity;
+    // slab mode appends the two halo layers behind the owned particles
+    const size_t slots = cap + 2 * (size_t)e->halo_capacity;
     e->slot_capacity = (int)slots;
-    // [0] = rest state (compact, last step's cell order), [1] = this step's snapshot (padded slots)
+    // [0] = rest state (compact, last step's cell order), [1] = this step's snapshot
     e->posw[0] = (float4*)take(cap * sizeof(float4));
     e->veli[0] = (float4*)take(cap * sizeof(float4));
     e->posw[1] = (float4*)take(slots * sizeof(float4));
@@ -859,7 +836,6 @@ static size_t engine_layout(gof_engine* e, char* base)
     e->cell_sorted = (int*)take(slots * sizeof(int));
     e->count = (int*)take(cells * sizeof(int));
     e->start = (int*)take(cells * sizeof(int));
-    e->pstart = (int*)take(cells * sizeof(int));
     e->tile_sums = (int*)take((size_t)(cdiv((int)cells, kScanTile) + 1) * sizeof(int));
     e->scalars = (StepScalars*)take(sizeof(StepScalars));
     char* sp = take(species_bytes(e->T));
@@ -915,17 +891,6 @@ extern "C" int gof_engine_set_graph(gof_engine* e, int enable)
 {
     if (!e) return fail(GOF_E_INVALID, "null engine");
     e->use_graph = enable != 0;
-    return 0;
-}
-
-extern "C" int gof_engine_set_kernel(gof_engine* e, int kernel)
-{
-    if (!e) return fail(GOF_E_INVALID, "null engine");
-    if (kernel != GOF_KERNEL_SCALAR && kernel != GOF_KERNEL_PACKED)
-        return fail(GOF_E_INVALID, "gof_engine_set_kernel: unknown kernel");
-    e->want_packed = kernel == GOF_KERNEL_PACKED;
-    e->binned = false;
-    ++e->generation;
     return 0;
 }
 
@@ -1032,46 +997,32 @@ static unsigned* engine_keys(gof_engine* e)
 #endif
 }
 
-// Which force kernel a step uses: the packed two-homes kernel needs every species pair to be
-// of the Clusters kind (its profile is evaluated branch-free for both homes at once).
-static bool engine_packed(const gof_engine* e)
-{
-    return e->want_packed && !e->species.has_boids && e->T <= kPackedMaxTypes;
-}
-
 // setup_bins on the resident state: posw[0]/veli[0]/acc (rest order) -> posw[1]/veli[1]
-// (cell order, velocities kicked by step1 when `kick`), cell tables filled.  For the packed
-// kernel the snapshot is laid out on even-padded cell segments and written a second time in
-// the duplicated layout.
+// (cell order, velocities kicked by step1 when `kick`), cell tables filled.
 static int engine_bin(gof_engine* e, bool kick, cudaStream_t st)
 {
     const Geometry& g = e->geom;
     const int n = e->n;
-    const bool packed = engine_packed(e);
     GOF_CUDA(cudaMemsetAsync(e->count, 0, (size_t)(g.num_cells + 2) * sizeof(int), st));
     MigrateOut none{};
     GOF_LAUNCH(k_hash_count<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->posw[0], e->veli[0], e->acc,
                (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, n, (const int*)nullptr, g,
                e->cell_of, e->off, e->count, none);
-    if (int rc = launch_scan<false>(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
-    if (packed)
-        if (int rc = launch_scan<true>(e->count, g.num_cells + 1, e->tile_sums, e->pstart, st)) return rc;
-    const int* layout = packed ? e->pstart : e->start;
+    if (int rc = launch_scan(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
+    const int* layout = e->start;
     GOF_LAUNCH(k_scatter_ids<false>, cdiv(n, kBinThreads), kBinThreads, 0, st, e->veli[0], n, (const int*)nullptr,
                e->cell_of, e->off, layout, e->slot_id, e->posw[0], engine_keys(e));
     GOF_LAUNCH(k_rank_gather_kick, cdiv(n, kBinThreads), kBinThreads, 0, st, n, (const int*)nullptr, e->cell_of,
                layout, e->count,
                e->slot_id, engine_keys(e), g.num_cells, e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1], e->cell_sorted,
-               packed ? 1 : 0, e->scalars, kick ? 1 : 0);
+               e->scalars, kick ? 1 : 0);
     e->binned = true;
-    e->binned_packed = packed;
     return 0;
 }
 
 // force (+ integrate) on the snapshot engine_bin just built
 static int engine_force(gof_engine* e, const ForceArgs& a, cudaStream_t st)
 {
-    if (engine_packed(e)) return launch_force2(e->geom, a, e->n + e->geom.num_cells, st);
     return launch_force(e->geom, a, e->species.kind(), kModeIntegrate, st);
 }
 
@@ -1082,7 +1033,7 @@ static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
     a->veli = e->veli[1];
     a->cell_sorted = e->cell_sorted;
     a->start = e->start;
-    a->pstart = engine_packed(e) ? e->pstart : e->start;
+    a->pstart = e->start;
     a->count = e->count;
     a->home_begin = 0;
     a->home_count = e->n;
@@ -1156,7 +1107,6 @@ static int engine_capture_step(gof_engine* e, float timestep, int wrap_mode)
     sg.timestep = timestep;
     sg.wrap_mode = wrap_mode;
     sg.split = g_force_split;
-    sg.packed = engine_packed(e);
     sg.generation = e->generation;
     sg.launches = launches;
     return 0;
@@ -1174,12 +1124,11 @@ extern "C" int gof_engine_step(gof_engine* e, int n_steps, float timestep, int w
         if (e->use_graph && !e->timing && !e->slab) {
             gof_engine::StepGraph& sg = e->graphs[e->parity];
             if (!sg.exec || sg.timestep != timestep || sg.wrap_mode != wrap_mode || sg.split != g_force_split ||
-                sg.packed != engine_packed(e) || sg.generation != e->generation)
+                sg.generation != e->generation)
                 if (int rc = engine_capture_step(e, timestep, wrap_mode)) return rc;
             GOF_CUDA(cudaGraphLaunch(sg.exec, st));
             g_launches.fetch_add((uint64_t)sg.launches, std::memory_order_relaxed);
             e->binned = true;
-            e->binned_packed = sg.packed;
         } else {
             if (int rc = engine_enqueue_step(e, timestep, wrap_mode, st, timed)) return rc;
         }
@@ -1261,7 +1210,7 @@ extern "C" int gof_engine_read_bins(gof_engine* e, int32_t* particle_bins, int32
     const int n = e->n;
     // posw[1]/veli[1] still hold the cell-ordered snapshot the last force kernel read
     GOF_LAUNCH(k_export_bins, cdiv(e->slot_capacity, kEwThreads), kEwThreads, 0, st, e->veli[1], e->cell_sorted,
-               e->start, e->binned_packed ? e->pstart : e->start, e->count, e->geom.num_cells, e->stage_bins,
+               e->start, e->start, e->count, e->geom.num_cells, e->stage_bins,
                e->stage_indices);
     if (particle_bins) GOF_CUDA(cudaMemcpyAsync(particle_bins, e->stage_bins, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
     if (particle_indices) GOF_CUDA(cudaMemcpyAsync(particle_indices, e->stage_indices, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
@@ -1475,18 +1424,17 @@ extern "C" int gof_slab_phase_sort_async(gof_engine* e, float timestep, void* st
                (const float*)nullptr, room, (const int*)words, g, e->cell_of + e->n_slots, e->off + e->n_slots,
                e->count, flag_only);
     GOF_LAUNCH(k_prepare_dt, 1, 1, 0, st, e->scalars, e->parity, timestep < 0 ? -1.0f : timestep);
-    if (int rc = launch_scan<false>(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
+    if (int rc = launch_scan(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
     GOF_LAUNCH(k_scatter_ids<false>, cdiv(bound, kBinThreads), kBinThreads, 0, st, e->veli[0], bound,
                (const int*)(words + 1), e->cell_of, e->off, e->start, e->slot_id, e->posw[0], engine_keys(e));
     GOF_LAUNCH(k_rank_gather_kick, cdiv(bound, kBinThreads), kBinThreads, 0, st, bound, (const int*)(words + 1),
                e->cell_of, e->start, e->count, e->slot_id, engine_keys(e), g.num_cells, e->posw[0], e->veli[0], e->acc,
                e->posw[1],
-               e->veli[1], e->cell_sorted, 0, e->scalars, 1);
+               e->veli[1], e->cell_sorted, e->scalars, 1);
     GOF_LAUNCH(k_slab_counts, 1, 1, 0, st, e->start, e->counters + 2, e->counters + 4, g.num_cells, g.nbx * g.nby,
                g.nlz - 2);
     e->n_slots = bound;  // upper bound until gof_slab_commit
     e->binned = true;
-    e->binned_packed = false;
     return 0;
 }
 

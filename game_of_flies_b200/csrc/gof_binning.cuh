@@ -151,14 +151,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total)
     return warp_prefix + inc - v;
 }
 
-// PAD2 = true scans the counts rounded up to even numbers: the padded cell starts of the
-// two-homes-per-lane force kernel (every cell segment gets an even number of slots so
-// that the two particles of a lane always share a cell).
-template <bool PAD2>
-__device__ __forceinline__ int scan_value(int v) { return PAD2 ? ((v + 1) & ~1) : v; }
-
 // Phase 1: sum of every tile of kScanTile counts.
-template <bool PAD2>
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_tile_sums(const int* __restrict__ in, int m, int* __restrict__ tile_sums)
 {
@@ -166,7 +159,7 @@ k_scan_tile_sums(const int* __restrict__ in, int m, int* __restrict__ tile_sums)
     int s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
-        if (base + k < m) s += scan_value<PAD2>(in[base + k]);
+        if (base + k < m) s += in[base + k];
     int total;
     block_exclusive_scan(s, total);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
@@ -190,7 +183,6 @@ k_scan_tile_prefix(int* __restrict__ tile_sums, int tiles)
 // Phase 3: scan inside each tile and add the tile prefix.  With a single tile
 // (up to 4096 cells: every configuration the reference UI can build) phases 1
 // and 2 are skipped and this is the whole scan.
-template <bool PAD2>
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_prefix,
              int* __restrict__ out)
@@ -200,7 +192,7 @@ k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_pre
     int s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        v[k] = (base + k < m) ? scan_value<PAD2>(in[base + k]) : 0;
+        v[k] = (base + k < m) ? in[base + k] : 0;
         s += v[k];
     }
     int total;
@@ -212,7 +204,7 @@ k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ tile_pre
     }
 }
 
-// Arrival-order scatter of the ids into the cell segments (`start` may be the padded table).
+// Arrival-order scatter of the ids into the cell segments.
 // The engine also scatters the sort key of the order INSIDE a cell: the bit pattern of x (x >= 0,
 // so the patterns order like the values); see k_rank_gather_kick.
 template <bool SOA>
@@ -261,7 +253,7 @@ struct StepScalars {
     int error;                      // sticky device-side error flags
 };
 
-constexpr float kDummyPos = 1e18f;  // a padding slot sits here: (1e18)^2 * 3 still fits fp32, never in range
+constexpr float kDummyPos = 1e18f;  // a padding entry of a candidate list sits here: (1e18)^2 * 3 still fits fp32, never in range
 
 // One thread per SOURCE particle (rest order): its rank in its cell is its slot in the cell's
 // segment.  The order inside a cell is by x, ties by id (`slot_key` given), or by id alone.  By x
@@ -281,7 +273,7 @@ k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict
                    int sentinel_cell, const float4* __restrict__ posw_in,
                    const float4* __restrict__ veli_in, const float4* __restrict__ acc_in,
                    float4* __restrict__ posw_out, float4* __restrict__ veli_out,
-                   int* __restrict__ cell_sorted, int padded,
+                   int* __restrict__ cell_sorted,
                    const StepScalars* __restrict__ scalars, int apply_kick)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,13 +320,6 @@ k_rank_gather_kick(int n, const int* __restrict__ n_limit, const int* __restrict
     posw_out[dst] = p;
     veli_out[dst] = v;
     cell_sorted[dst] = c;
-    if (padded && rank == cnt - 1 && (cnt & 1)) {
-        // the padding slot of an odd cell: far away, type 0 (a valid table index), never a home
-        const float D = kDummyPos;
-        posw_out[dst + 1] = make_float4(D, D, D, __int_as_float(0));
-        veli_out[dst + 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        cell_sorted[dst + 1] = c;
-    }
 }
 
 }  // namespace gof

@@ -33,7 +33,7 @@ def _any_ptr(x) -> int:
 
 class ParticleEngine:
     def __init__(self, num_particles: int, parameter_matrix: np.ndarray, limits, r_max: float,
-                 device=None, wrap_mode: int = _lib.WRAP_REFERENCE, packed: bool = False):
+                 device=None, wrap_mode: int = _lib.WRAP_REFERENCE):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
         self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -53,8 +53,6 @@ class ParticleEngine:
         self._arena_ptr = (base + 255) // 256 * 256
         _lib.check(self.lib.gof_engine_bind_arena(self._handle, self._arena_ptr, nbytes))
         self.arena_bytes = nbytes
-        if packed:
-            _lib.check(self.lib.gof_engine_set_kernel(self._handle, _lib.KERNEL_PACKED))
 
     # -- helpers ---------------------------------------------------------------------------
     def _stream(self) -> int:

@@ -190,19 +190,11 @@ int gof_engine_snapshot_copy(gof_engine *e, float *xyz_any, void *stream);
 int gof_engine_read_bins(gof_engine *e, int32_t *particle_bins_any, int32_t *bin_counts_any,
                          int32_t *bin_starts_any, int32_t *particle_indices_any, void *stream);
 
-/* Force-kernel selection.  GOF_KERNEL_SCALAR (default): one home particle per lane, any mix
- * of Clusters and Boids species.  GOF_KERNEL_PACKED: two home particles per lane with packed
- * fp32 arithmetic; used only while every species pair is of the Clusters kind, otherwise the
- * engine falls back to the scalar kernel.  Results agree to fp32 rounding. */
-#define GOF_KERNEL_SCALAR 0
-#define GOF_KERNEL_PACKED 1
-int gof_engine_set_kernel(gof_engine *e, int kernel);
-
 /* gof_engine_step launches every step as one CUDA graph (captured on first use, per timestep
  * value and wrap mode); enable = 0 goes back to individual kernel launches.  Same results. */
 int gof_engine_set_graph(gof_engine *e, int enable);
 
-/* Small-system tuning knob of the scalar kernel (process-wide).  For Clusters-kind systems the
+/* Small-system tuning knob of the force kernel (process-wide).  For Clusters-kind systems the
  * 9 (3 in 2D) stencil rows of a home particle can be walked by 3 or 9 warps instead of one
  * thread; -1 (default) picks by system size.  Results are bit-identical whatever the value. */
 int gof_set_force_split(int split);

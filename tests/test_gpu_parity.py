@@ -166,19 +166,18 @@ def test_accelerator_random_states(gof, kinds, counts, limits, speed, wrap_mode)
     check_accelerator(gof, st, wrap_mode)
 
 
-def engine_from_state(gof, st, wrap_mode=orc.WRAP_REFERENCE, packed=False):
-    e = gof.eng.ParticleEngine(st["n"], st["parameter_matrix"], st["limits"], st["r_max"], wrap_mode=wrap_mode,
-                               packed=packed)
+def engine_from_state(gof, st, wrap_mode=orc.WRAP_REFERENCE):
+    e = gof.eng.ParticleEngine(st["n"], st["parameter_matrix"], st["limits"], st["r_max"], wrap_mode=wrap_mode)
     e.upload([st["pos"][k].astype(np.float32) for k in range(3)], st["types"],
              vel=[st["vel"][k].astype(np.float32) for k in range(3)],
              acc=[st["acc"][k].astype(np.float32) for k in range(3)])
     return e
 
 
-def check_engine_step(gof, st, ts, wrap_mode=orc.WRAP_REFERENCE, packed=False):
+def check_engine_step(gof, st, ts, wrap_mode=orc.WRAP_REFERENCE):
     o = oracle_sim(st, timestep=ts, wrap_mode=wrap_mode)
     used = o.core_step()
-    e = engine_from_state(gof, st, wrap_mode, packed)
+    e = engine_from_state(gof, st, wrap_mode)
     e.step(1, ts)
     out = e.download(pos=True, vel=True, acc=True)
     pb, cnt, stt, idx = e.read_bins()
@@ -213,7 +212,6 @@ def test_engine_step_on_golden_states(gof, path):
     for s in (0, steps - 1):
         st, ts, _ = golden_state(path, s)
         check_engine_step(gof, st, ts)
-        check_engine_step(gof, st, ts, packed=True)
 
 
 @pytest.mark.parametrize("kinds,counts,limits,speed,ts", [
@@ -227,9 +225,6 @@ def test_engine_step_random_states(gof, kinds, counts, limits, speed, ts):
     st = random_state(counts, limits, seed=23, kinds=kinds, speed=speed)
     check_engine_step(gof, st, ts)
     check_engine_step(gof, st, ts, wrap_mode=orc.WRAP_MINIMAGE)
-    # the packed two-homes-per-lane kernel (Clusters only; other kinds fall back to the scalar one)
-    check_engine_step(gof, st, ts, packed=True)
-    check_engine_step(gof, st, ts, wrap_mode=orc.WRAP_MINIMAGE, packed=True)
 
 
 @pytest.mark.parametrize("wrap_mode", [orc.WRAP_REFERENCE, orc.WRAP_MINIMAGE], ids=["refwrap", "minimage"])
