@@ -76,6 +76,7 @@ SIGNATURES = {
     "gof_engine_set_graph": (_i, [_vp, _i]),
     "gof_engine_timing": (_i, [_vp, _i]),
     "gof_engine_force_time": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
+    "gof_engine_pair_stats": (_i, [_vp, _i, _vp, _vp]),
     "gof_engine_last_timestep": (_i, [_vp, C.POINTER(_f), _vp]),
     "gof_slab_create": (_i, [C.POINTER(_vp), _i, _i, _i, C.POINTER(Grid), _vp, _i, _i, _i, _i]),
     "gof_slab_upload": (_i, [_vp, _i] + [_vp] * 11 + [_vp]),

@@ -37,8 +37,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
              "-shared", "-Xcompiler", "-fPIC"]
     if verbose:
         flags += ["-Xptxas", "-v"]
-    cmd = [nvcc_path(), *flags, *SOURCES, "-o", LIB]
-    subprocess.run(cmd, check=True)
+    # write next to the target and rename: a snapshot of the tree (gpurun) never sees half a library
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc_path(), *flags, *SOURCES, "-o", tmp]
+    try:
+        subprocess.run(cmd, check=True)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB
 
 

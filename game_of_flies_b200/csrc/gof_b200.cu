@@ -285,12 +285,12 @@ static int upload_species(const HostSpecies& h, const DeviceSpecies& d, cudaStre
 
 static size_t force_smem_bytes(int T, int kind, int split)
 {
-    const size_t TA = (size_t)(T | 1);
-    return (size_t)T * T * sizeof(PairParam) + (size_t)T * TA * (sizeof(float4) + sizeof(float2)) + 16 +
+    return (size_t)T * T * sizeof(PairParam) + (size_t)T * kRowBytes +
            (kind != kKindClusters ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0) +
            (kind == kKindBoids ? (size_t)kQueueDepth * kForceThreads * sizeof(unsigned) : 0) +
            (split > 1 ? (size_t)kSplitRuns * 3 * kSplitHomes * sizeof(float) : 0) +
-           (kind == kKindClusters ? (size_t)(split > 1 ? split : kForceThreads / 32) * kListLen * (sizeof(float4) + sizeof(int)) : 0);
+           (kind == kKindClusters ? (split > 1 ? (size_t)split * kListLen * (sizeof(float4) + sizeof(int))
+                                               : (size_t)(kForceThreads / 32) * kWarpGroupBytes) : 0);
 }
 
 // cudaFuncSetAttribute is per device: remember per kernel instantiation which devices have it
@@ -1217,6 +1217,29 @@ extern "C" int gof_engine_read_bins(gof_engine* e, int32_t* particle_bins, int32
     const size_t cb = (size_t)e->geom.num_cells * sizeof(int);
     if (bin_counts) GOF_CUDA(cudaMemcpyAsync(bin_counts, e->count, cb, cudaMemcpyDefault, st));
     if (bin_starts) GOF_CUDA(cudaMemcpyAsync(bin_starts, e->start, cb, cudaMemcpyDefault, st));
+    return 0;
+}
+
+/* Diagnostics for bench.py: stencil candidates, force evaluations and pairs in range, summed
+ * over the particles of the snapshot the last step / accelerate read (see k_pair_stats).
+ * Synchronises `stream`. */
+extern "C" int gof_engine_pair_stats(gof_engine* e, int wrap_mode, unsigned long long* out3, void* stream)
+{
+    if (int rc = engine_ready(e, true)) return rc;
+    if (!out3) return fail(GOF_E_INVALID, "gof_engine_pair_stats: null output");
+    if (!e->binned) return fail(GOF_E_STATE, "gof_engine_pair_stats: no step or accelerate has run since the upload");
+    if (e->n <= 0) { out3[0] = out3[1] = out3[2] = 0; return 0; }
+    cudaStream_t st = (cudaStream_t)stream;
+    // the slot/rank scratch is free between steps: borrow three 64-bit words of it
+    PairStats* d = reinterpret_cast<PairStats*>(e->slot_id);
+    GOF_CUDA(cudaMemsetAsync(d, 0, sizeof(PairStats), st));
+    GOF_LAUNCH(k_pair_stats, cdiv(e->n, kForceThreads), kForceThreads, 0, st, e->geom, (const float4*)e->posw[1],
+               (const int*)e->cell_sorted, (const int*)e->start, (const int*)e->count, e->n, wrap_mode,
+               e->species.kind() == kKindClusters ? 1 : 0, d);
+    PairStats hst{};
+    GOF_CUDA(cudaMemcpyAsync(&hst, d, sizeof(PairStats), cudaMemcpyDeviceToHost, st));
+    GOF_CUDA(cudaStreamSynchronize(st));
+    out3[0] = hst.candidates; out3[1] = hst.evaluated; out3[2] = hst.in_range;
     return 0;
 }
 

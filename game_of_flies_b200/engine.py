@@ -167,6 +167,13 @@ class ParticleEngine:
         _lib.check(self.lib.gof_engine_force_time(self._handle, C.byref(ms), C.byref(k)))
         return float(ms.value), int(k.value)
 
+    def pair_stats(self) -> dict:
+        """Per-launch totals of the neighbour search on the last step's snapshot (diagnostics for
+        bench.py): stencil candidates, force evaluations after culling, pairs really in range."""
+        out = (C.c_ulonglong * 3)()
+        _lib.check(self.lib.gof_engine_pair_stats(self._handle, self.wrap_mode, out, self._stream()))
+        return {"n": self.n, "candidates": int(out[0]), "evaluated": int(out[1]), "in_range": int(out[2])}
+
     def candidate_pairs(self) -> int:
         """Distance tests the force kernel performs for the current binning: for every particle
         the population of its 9 / 27 stencil cells (host arithmetic on the cell counts)."""

@@ -206,6 +206,12 @@ int gof_set_force_split(int split);
 int gof_engine_timing(gof_engine *e, int enable);
 int gof_engine_force_time(gof_engine *e, float *total_ms, int *launches);
 
+/* Diagnostics behind bench.py's roofline block (never part of a step): for the cell-ordered
+ * snapshot the last step / accelerate read, out3 = {stencil candidates, force evaluations the
+ * kernel spends after culling, pairs closer than r_max}, each summed over the particles (the
+ * owned particles in slab mode; halo cells count as candidates).  Synchronises `stream`. */
+int gof_engine_pair_stats(gof_engine *e, int wrap_mode, unsigned long long *out3, void *stream);
+
 /* The timestep the last step used (synchronises `stream`). */
 int gof_engine_last_timestep(gof_engine *e, float *out, void *stream);
 

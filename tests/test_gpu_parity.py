@@ -418,6 +418,76 @@ def test_recorder_pipeline_writes_the_same_frames_as_stepwise_updates(gof, tmp_p
     assert np.array_equal(state["type_array"][: int(state["num_particles"])], a.particle_type_index_array)
 
 
+def check_full_field(gof, st, wrap_mode, label):
+    """Whole-system parity at a BASELINE size: every particle's bin, the bin tables, the sorted
+    order and the whole acceleration field of the state, then one full step, against the oracle
+    (all host threads: its float64 atomics make the summation order vary at the 1e-16 level)."""
+    from parity_util import acc_error_unfloored
+    threads = orc.max_threads()
+    o = oracle_sim(st, wrap_mode=wrap_mode, n_threads=threads)
+    o.setup_bins()
+    o.accelerate()
+    want = np.stack([o.acc_x, o.acc_y, o.acc_z])
+    e = engine_from_state(gof, st, wrap_mode)
+    e.accelerate()
+    got = e.download(pos=False, acc=True)["acc"]
+    pb, cnt, stt, idx = e.read_bins()
+    cells = o.grid["num_cells"]
+    assert np.array_equal(pb, o.particle_bins)
+    assert np.array_equal(cnt, o.particle_bin_counts[:cells])
+    assert np.array_equal(stt, o.particle_bin_starts[:cells])
+    assert np.array_equal(idx, o.particle_indices)
+    mx, rms = acc_errors(got, want)
+    raw = acc_error_unfloored(got, want)
+    print(f"[{label}] N={st['n']} acceleration error: max {mx:.3e} (rms {rms:.3e}) relative to "
+          f"max(|a_i|, median|a|); unfloored max |da_i|/|a_i| {raw:.3e}")
+    assert mx <= ACC_RTOL, f"{label}: acceleration error {mx:.3e} (rms {rms:.3e})"
+    e.close()
+    # one full step (adaptive timestep) from the same state
+    o2 = oracle_sim(st, timestep=None, wrap_mode=wrap_mode, n_threads=threads)
+    used = o2.core_step()
+    e = engine_from_state(gof, st, wrap_mode)
+    e.step(1)
+    out = e.download(pos=True, vel=True, acc=True)
+    assert e.last_timestep() == pytest.approx(used, rel=1e-6)
+    mx2, _ = acc_errors(out["acc"], np.stack([o2.acc_x, o2.acc_y, o2.acc_z]))
+    assert mx2 <= ACC_RTOL
+    a_scale = np.abs(np.stack([o2.acc_x, o2.acc_y, o2.acc_z])).max() + 1.0
+    assert np.abs(out["vel"] - np.stack([o2.vel_x, o2.vel_y, o2.vel_z])).max() <= 2e-5 * a_scale * used + 1e-5
+    dx = np.abs(out["pos"] - np.stack([o2.pos_x, o2.pos_y, o2.pos_z]))
+    L = st["limits"][:, None]
+    dx = np.where(L > 0, np.minimum(dx, np.abs(L - dx)), dx)
+    assert dx.max() <= 4 * np.spacing(np.float32(st["limits"].max())) + 1e-5 * a_scale * used * used
+    e.close()
+    return mx, raw
+
+
+@pytest.mark.parametrize("wrap_mode", [orc.WRAP_REFERENCE, orc.WRAP_MINIMAGE], ids=["refwrap", "minimage"])
+def test_full_size_clusters3d_1m_whole_field(gof, wrap_mode):
+    """BASELINE.json configs[1] (Clusters 3D, 5 species, N=1M, density of the reference's 3D run):
+    the WHOLE field and the bins against the oracle, both wrap modes, no particle left out."""
+    n_per = 200_000
+    L = float((5 * n_per / 0.014) ** (1.0 / 3.0))
+    st = random_state([n_per] * 5, (L, L, L), seed=1, kinds="clusters", speed=2.0)
+    check_full_field(gof, st, wrap_mode, "clusters3d_1m")
+
+
+def test_full_size_boids3d_4m_whole_field(gof):
+    """BASELINE.json configs[2] (Boids 3D, N=4M): whole field, bins, exact neighbour structure
+    (a wrong neighbour count shows as an O(1) error in cohesion / alignment), one full step."""
+    n_per = 4_000_000 // 3
+    st = random_state([n_per] * 3, (660.0, 660.0, 660.0), seed=2, kinds="boids", speed=8.0)
+    check_full_field(gof, st, orc.WRAP_REFERENCE, "boids3d_4m")
+
+
+def test_full_size_mixed3d_8sp_1m_whole_field(gof):
+    """BASELINE.json configs[3]'s species mix (Clusters+Boids, 8 species) at N=1M on one GPU."""
+    n_per = 125_000
+    L = float((8 * n_per / 0.014) ** (1.0 / 3.0))
+    st = random_state([n_per] * 8, (L, L, L), seed=3, kinds="mixed", speed=6.0)
+    check_full_field(gof, st, orc.WRAP_REFERENCE, "mixed3d_8sp_1m")
+
+
 def test_full_size_properties_clusters3d_1m(gof):
     """BASELINE.json configs[1] (Clusters 3D, 5 species, N=1M): size-independent properties."""
     n_per = 200_000
@@ -464,8 +534,8 @@ def test_full_size_properties_clusters3d_1m(gof):
 
 
 def test_full_size_properties_boids3d_4m(gof):
-    """BASELINE.json configs[2] (Boids 3D, N=4M): size-independent properties + sampled brute force
-    of the per-type neighbour counts (exact integers) that drive cohesion / alignment."""
+    """BASELINE.json configs[2] (Boids 3D, N=4M): size-independent properties after two steps (the
+    oracle comparison of the same system is test_full_size_boids3d_4m_whole_field)."""
     n_per = 4_000_000 // 3
     st = random_state([n_per] * 3, (660.0, 660.0, 660.0), seed=2, kinds="boids", speed=8.0)
     e = engine_from_state(gof, st)
