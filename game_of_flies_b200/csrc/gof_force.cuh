@@ -58,6 +58,10 @@ struct ForceArgs {
     // Slab mode, interior launch: the range is not known on the host yet; it is derived from
     // the device words {live, bottom layer population, top layer population} (null otherwise).
     const int* interior_words;
+    // Slab mode, boundary launch with the sizes still on the device (peer-memory transport): the two
+    // ranges are [0, lo) and [live - hi, live) from the same words; home_count is an upper bound
+    // of lo + hi for the grid.
+    const int* boundary_words;
     const PairParam* table;   // [T*T]
     const unsigned* kind_rows;  // [T] bit j of row i set => (i, j) is of Boids kind
     const double* sep_exact;  // [T*T] args[0] / 5 in float64 (guard band of the separation radius)
@@ -688,224 +692,6 @@ __device__ __forceinline__ void walk_image(Home& h, RowAddr tabrow_s, const Pair
         walk_culled<false, false>(h, tabrow_s, tabrow, a, g, im, b, sx, sy, sz, s, e, lst, 0u, 0);
 }
 
-// ---- Clusters kind, one thread per particle: four groups of eight lanes, each on its own walk ---
-// The whole-warp walk above evaluates every candidate that is in reach of the box of 32 home
-// particles: about one cell (1 x 0.94 x 0.94 bins), i.e. ~600 of the ~820 candidates of a stencil,
-// for ~130 real neighbours.  Eight consecutive particles of the (x-ordered) cell span a quarter of
-// that box (0.23 x 0.78 x 0.78 bins: the y and z ranges of eight particles are well inside the
-// cell): ~360 candidates.  So every aligned group of eight lanes of a warp walks ON ITS OWN: its own
-// box, its own runs (the cells around ITS home cells), its own ring of survivors in shared memory.
-// The four groups must not wait for each other per run (their survivor counts differ by +-15 % per
-// run, but only by a few % over the whole stencil), so each group is a small producer / consumer
-// pipeline over its list of runs, and the warp only alternates between two warp-uniform phases:
-//   fetch  while some group has fewer than four survivors left: every group with room in its ring
-//          tests the next 32 candidates of its current run (four per lane) against its box and
-//          appends the survivors, in order; a run that ends is padded to a multiple of four with
-//          parked particles, and every block of four carries the index of its run (a tag)
-//   eval   every group that has a block evaluates it: the four candidates against the eight home
-//          particles of the group, exactly like walk_group
-// A lane still meets a superset of its own candidates in run order, run by run, and what it skips
-// is out of its range: the fused multiply-add chains, the per-run partial sums and their folding
-// order are those of every other walk, so the result does not depend on the grouping.
-constexpr int kGroupRing = 64;     // survivors a group can hold (a power of two)
-constexpr int kGroupFetch = 32;    // candidates a group tests per fetch round (four per lane)
-constexpr int kRunSlots = 27;      // 9 stencil rows x {main run, cell across the low x edge, cell across the high x edge}
-constexpr unsigned kGroupRingBytes = kGroupRing * 16u;
-constexpr unsigned kGroupTagBytes = (kGroupRing / 4) * 4u;
-constexpr unsigned kGroupRunBytes = kRunSlots * 16u;  // {first slot, end slot, packed shifts, -}
-constexpr unsigned kGroupBytes = kGroupRingBytes + kGroupTagBytes + kGroupRunBytes;
-constexpr unsigned kWarpGroupBytes = 4u * kGroupBytes;
-static_assert(kGroupBytes % 16u == 0u, "group blocks hold float4 rings");
-
-__device__ __forceinline__ void sts1(unsigned saddr, int v)
-{
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ int lds1v(unsigned saddr)
-{
-    int v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
-    return v;
-}
-__device__ __forceinline__ int4 lds4iv(unsigned saddr)
-{
-    int4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"(saddr)
-                 : "memory");
-    return v;
-}
-
-// `gmem`: shared-memory address of this lane's group block (ring, tags, run table).  All lanes of
-// the warp are converged here, every group sits in one row of cells (cy, lz), no lane is on the
-// literal z-wrap path.  Returns the acceleration in h.ax, h.ay, h.az.
-__device__ __forceinline__ void walk_groups(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
-                                            const ForceArgs& a, const Geometry& g, int cx, int cy, int lz, int gz,
-                                            int skip_dz, unsigned gmem)
-{
-    constexpr unsigned kFull = 0xffffffffu;
-    const unsigned lane = (unsigned)lane_id(), l8 = lane & 7u, gsh = lane & 24u;
-    const unsigned below8 = (1u << l8) - 1u;
-    const unsigned ring = gmem, tags = gmem + kGroupRingBytes, runs = tags + kGroupTagBytes;
-
-    // the group's box and range of home cells (xor butterflies stay inside aligned groups of eight)
-    float blox = h.x, bhix = h.x, bloy = h.y, bhiy = h.y, bloz = h.z, bhiz = h.z;
-    int cxl = cx, cxh = cx;
-#pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
-        blox = fminf(blox, __shfl_xor_sync(kFull, blox, d));
-        bhix = fmaxf(bhix, __shfl_xor_sync(kFull, bhix, d));
-        bloy = fminf(bloy, __shfl_xor_sync(kFull, bloy, d));
-        bhiy = fmaxf(bhiy, __shfl_xor_sync(kFull, bhiy, d));
-        bloz = fminf(bloz, __shfl_xor_sync(kFull, bloz, d));
-        bhiz = fmaxf(bhiz, __shfl_xor_sync(kFull, bhiz, d));
-        cxl = min(cxl, __shfl_xor_sync(kFull, cxl, d));
-        cxh = max(cxh, __shfl_xor_sync(kFull, cxh, d));
-    }
-
-    // ---- the group's runs, in the order every walk goes through them: per stencil row the
-    // un-shifted cells cxl - 1 .. cxh + 1, then the cell across the low x edge, then the one
-    // across the high x edge.  Lane r of the group fills row r (lane 0 also row 8).
-    const int nrows = g.is3d ? 9 : 3;
-    for (int r = (int)l8; r < nrows; r += 8) {
-        const int dzi = g.is3d ? r / 3 - 1 : 0, dyi = g.is3d ? r % 3 - 1 : r - 1;
-        int nl = lz + dzi, sz = 0;
-        if (g.is3d) {
-            const int ngz = gz + dzi;
-            if (ngz < 0) { sz = 1; if (g.index_wrap_z) nl += g.nbz; }
-            else if (ngz >= g.nbz) { sz = -1; if (g.index_wrap_z) nl -= g.nbz; }
-        }
-        const bool skip = g.is3d && dzi == skip_dz;  // across the z boundary, reference wrap: no interaction
-        int ny = cy + dyi, sy = 0;
-        if (ny < 0) { ny += g.nby; sy = 1; }
-        else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
-        const int rb = (nl * g.nby + ny) * g.nbx;
-        const int lo = cxl > 0 ? cxl - 1 : 0;
-        const int hi = cxh < g.nbx - 1 ? cxh + 1 : g.nbx - 1;
-        int s0 = 0, e0 = 0, s1 = 0, e1 = 0, s2 = 0, e2 = 0;
-        if (!skip) {
-            s0 = a.pstart[rb + lo];
-            e0 = a.pstart[rb + hi] + a.count[rb + hi];
-            if (cxl == 0) { s1 = a.pstart[rb + g.nbx - 1]; e1 = s1 + a.count[rb + g.nbx - 1]; }
-            if (cxh == g.nbx - 1) { s2 = a.pstart[rb]; e2 = s2 + a.count[rb]; }
-        }
-        const unsigned at = runs + (unsigned)(3 * r) * 16u;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(at), "r"(s0), "r"(e0), "r"(pack_shifts(0, sy, sz)), "r"(0) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(at + 16u), "r"(s1), "r"(e1), "r"(pack_shifts(1, sy, sz)), "r"(0) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(at + 32u), "r"(s2), "r"(e2), "r"(pack_shifts(-1, sy, sz)), "r"(0) : "memory");
-    }
-    __syncwarp();
-    const int nruns = 3 * nrows;
-
-    // producer state (the same in the eight lanes of a group)
-    int ri = -1, j = 0, e = 0;
-    bool fdone = false;
-    float lox = 0.f, hix = 0.f, loy = 0.f, hiy = 0.f, loz = 0.f, hiz = 0.f;  // the box as the current run sees it
-    auto advance = [&]() {
-        for (;;) {
-            ++ri;
-            if (ri >= nruns) { fdone = true; j = e = 0; break; }
-            const int4 en = lds4iv(runs + (unsigned)ri * 16u);
-            if (en.x < en.y) {
-                j = en.x; e = en.y;
-                const float tx = (float)((en.z & 3) - 1) * g.Lx, ty = (float)(((en.z >> 2) & 3) - 1) * g.Ly,
-                            tz = (float)(((en.z >> 4) & 3) - 1) * g.Lz;
-                lox = blox + tx - g.cull_slack; hix = bhix + tx + g.cull_slack;
-                loy = bloy + ty - g.cull_slack; hiy = bhiy + ty + g.cull_slack;
-                loz = bloz + tz - g.cull_slack; hiz = bhiz + tz + g.cull_slack;
-                break;
-            }
-        }
-    };
-    advance();
-    unsigned head = 0u, tail = 0u;  // ring positions in entries, ever increasing; head stays a multiple of four
-
-    // consumer state
-    int crun = -1;
-    Image im = make_image(h, g, 0, 0, 0);
-    float3 rep = make_float3(0.0f, 0.0f, 0.0f);
-    float totx = 0.0f, toty = 0.0f, totz = 0.0f;
-    h.ax = h.ay = h.az = 0.0f;  // the current run's own accumulator
-    auto fold = [&]() {  // total = (run + its corrections) + total, like every other walk
-        h.ax += rep.x; h.ay += rep.y; h.az += rep.z;
-        totx = h.ax + totx; toty = h.ay + toty; totz = h.az + totz;
-        h.ax = h.ay = h.az = 0.0f;
-        rep = make_float3(0.0f, 0.0f, 0.0f);
-    };
-
-    for (;;) {
-        const int len = (int)(tail - head);
-        if (__any_sync(kFull, !fdone && len < 4)) {
-            // ---- fetch round: every group that has room tests the next 32 candidates of its run
-            const bool want = !fdone && len <= kGroupRing - kGroupFetch - 4;
-            float4 p[4];
-            bool keep[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int jj = j + 8 * i + (int)l8;
-                keep[i] = want && jj < e;
-                p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (keep[i]) p[i] = ldg4(a.posw + jj);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float ex = fmaxf(fmaxf(lox - p[i].x, p[i].x - hix), 0.0f);
-                const float ey = fmaxf(fmaxf(loy - p[i].y, p[i].y - hiy), 0.0f);
-                const float ez = fmaxf(fmaxf(loz - p[i].z, p[i].z - hiz), 0.0f);
-                keep[i] = keep[i] && fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < g.cull_r2;
-            }
-            unsigned pos = tail;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const unsigned m = (__ballot_sync(kFull, keep[i]) >> gsh) & 0xffu;
-                if (keep[i]) {
-                    const unsigned at = pos + __popc(m & below8);
-                    sts4(ring + ((at & (kGroupRing - 1)) << 4), p[i]);
-                    if ((at & 3u) == 0u) sts1(tags + (((at >> 2) & (kGroupRing / 4 - 1)) << 2), ri);
-                }
-                pos += __popc(m);
-            }
-            if (want) {
-                tail = pos;
-                j += kGroupFetch;
-                if (j >= e) {  // the run is through: close its last block, move on to the next run
-                    const unsigned pad = (0u - tail) & 3u;
-                    if (l8 < pad)
-                        sts4(ring + (((tail + l8) & (kGroupRing - 1)) << 4),
-                             make_float4(kDummyPos, kDummyPos, kDummyPos, 0.0f));
-                    tail += pad;
-                    advance();
-                }
-            }
-            __syncwarp();
-            continue;
-        }
-        // ---- eval: every group that is not through has at least one block here
-        const bool have = len >= 4;
-        if (!__any_sync(kFull, have)) break;
-        const unsigned at = ring + ((head & (kGroupRing - 1)) << 4);
-        if (have) {
-            const int tag = lds1v(tags + (((head >> 2) & (kGroupRing / 4 - 1)) << 2));
-            if (tag != crun) {  // the block opens another run of this group
-                if (crun >= 0) fold();
-                crun = tag;
-                const int code = lds4iv(runs + (unsigned)tag * 16u).z;
-                if (code != im.shifts) im = make_image(h, g, (code & 3) - 1, ((code >> 2) & 3) - 1, ((code >> 4) & 3) - 1);
-            }
-        }
-        const bool lowfix = __any_sync(kFull, have && im.up);
-        if (have) {
-            if (lowfix) walk_group<false, true>(h, rep, tabrow_s, tabrow, g, im, at, 0u, 0, 0, 0);
-            else walk_group<false, false>(h, rep, tabrow_s, tabrow, g, im, at, 0u, 0, 0, 0);
-            head += 4u;
-        }
-        __syncwarp();  // the block is read before a later fetch round may overwrite it
-    }
-    fold();
-    h.ax = totx; h.ay = toty; h.az = totz;
-}
-
 // Choice of the LOWFIX variant for the lanes that are converged here (every lane of a code
 // path walks the same sequence of runs, possibly empty).  The variant does not change a
 // lane's result when its own `lo` parts are zero, so the vote only saves instructions.
@@ -1289,16 +1075,12 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     char* behind = tabAB + T * kRowBytes;
     float* boid_acc = reinterpret_cast<float*>(behind) + threadIdx.x;
     float* part = reinterpret_cast<float*>(behind) + hl;  // SPLIT > 1 only
-    // Clusters kind, behind `part`.  SPLIT == 1: every warp's four group blocks (walk_groups); the
-    // literal z-wrap walk of a whole warp (quirk_walk) keeps its survivor list and the list of
-    // their slots in the same bytes.  SPLIT > 1: every warp's survivor list (walk_culled), and
-    // behind all the lists those of their slots.
+    // Clusters kind, behind `part`: every warp's list of surviving candidates (walk_culled) and,
+    // behind all the lists, those of their slots (literal z-wrap walk only)
     const unsigned wmem = (unsigned)__cvta_generic_to_shared(behind) +
                           (SPLIT > 1 ? kSplitRuns * 3 * kSplitHomes * 4u : 0u);
-    const unsigned lst = wmem + (threadIdx.x >> 5) * (SPLIT > 1 ? kListLen * 16u : kWarpGroupBytes);
-    const unsigned lst_j = SPLIT > 1 ? wmem + (blockDim.x >> 5) * (kListLen * 16u) + (threadIdx.x >> 5) * (kListLen * 4u)
-                                     : lst + kListLen * 16u;
-    static_assert(kWarpGroupBytes >= kListLen * 20u, "quirk_walk's lists live in the warp's group blocks");
+    const unsigned lst = wmem + (threadIdx.x >> 5) * (kListLen * 16u);
+    const unsigned lst_j = wmem + (blockDim.x >> 5) * (kListLen * 16u) + (threadIdx.x >> 5) * (kListLen * 4u);
     for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
         const PairParam pp = a.table[q];
         tab[q] = pp;
@@ -1318,11 +1100,20 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     __syncthreads();
 
     int home_begin = a.home_begin, home_count = a.home_count;
+    int home_begin2 = a.home_begin2, home_count2 = a.home_count2;
     if (a.interior_words) {  // owned particles that are in neither boundary layer
         const int live = a.interior_words[0], lo = a.interior_words[1], hi = a.interior_words[2];
         home_begin = lo;
         home_count = live - lo - hi;
         if (home_count <= 0) return;  // (block-uniform: one or two owned layers)
+    }
+    if (a.boundary_words) {  // the bottom and the top owned layer
+        const int live = a.boundary_words[0], lo = a.boundary_words[1], hi = a.boundary_words[2];
+        home_begin = 0;
+        home_count = lo;
+        home_begin2 = live - hi;
+        home_count2 = hi;
+        if (lo + hi <= 0) return;
     }
     // Block -> particles mapping, rotated so that the blocks of the TOP z layer run first, then the
     // bottom layer, then the rest: in GOF_WRAP_REFERENCE mode those two layers take the literal path
@@ -1337,7 +1128,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     // layers apart.)
     int blk = (int)blockIdx.x;
 #ifndef GOF_NO_ROTATE
-    if (g.is3d && g.index_wrap_z && a.wrap_mode == kWrapReference && a.home_count2 == 0 && !a.interior_words) {
+    if (g.is3d && g.index_wrap_z && a.wrap_mode == kWrapReference && home_count2 == 0 && !a.interior_words) {
         const int grid = (int)gridDim.x;
         const int top0 = (a.pstart[(g.nlz - 1) * g.nbx * g.nby] - home_begin) / kHomes;  // first block of the top layer
         const int n_top = grid - top0;
@@ -1370,10 +1161,11 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
 #endif
     const int local = blk * kHomes + hl;
     if (a.interior_words && local - hl >= home_count) return;  // whole block past the range
-    const bool valid = local < home_count + a.home_count2;
+    if (a.boundary_words && local - hl >= home_count + home_count2) return;
+    const bool valid = local < home_count + home_count2;
     int k = home_begin + (local < home_count ? local : home_count - 1);
-    if (local >= home_count && a.home_count2 > 0)
-        k = a.home_begin2 + (valid ? local - home_count : a.home_count2 - 1);
+    if (local >= home_count && home_count2 > 0)
+        k = home_begin2 + (valid ? local - home_count : home_count2 - 1);
 
     const float4 pi = a.posw[k];
     const float4 vi = a.veli[k];
@@ -1430,25 +1222,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     if (KIND == kKindClusters)  // (one row of cells: one layer, so `quirk` is the same for all lanes)
         as_warp = __reduce_min_sync(0xffffffffu, (unsigned)cyz) == __reduce_max_sync(0xffffffffu, (unsigned)cyz);
 #endif
-    // Clusters kind, one thread per particle: when every aligned group of eight lanes sits in one
-    // row of cells and no lane is on the literal z-wrap path, the four groups walk on their own
-    // (walk_groups).  That covers every warp the whole-warp walk below would take, so that walk is
-    // only compiled for the split variants.
-    bool as_groups = false;
-#ifndef GOF_NO_GROUP_WALK
-    if (KIND == kKindClusters && SPLIT == 1) {
-        int rlo = cyz, rhi = cyz;
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
-            rlo = min(rlo, __shfl_xor_sync(0xffffffffu, rlo, d));
-            rhi = max(rhi, __shfl_xor_sync(0xffffffffu, rhi, d));
-        }
-        as_groups = __all_sync(0xffffffffu, rlo == rhi && !quirk);
-    }
-#endif
-    if (as_groups) {
-        walk_groups(h, tabrow_s, tabrow, a, g, cx, cy, lz, gz, skip_dz, lst + (((unsigned)threadIdx.x >> 3) & 3u) * kGroupBytes);
-    } else if (as_warp && quirk) {
+    if (as_warp && quirk) {
         // bottom / top layer in GOF_WRAP_REFERENCE mode: the same walk by the literal rules, out of line
         const Box box = warp_box(h);
         const int cx_min = (int)__reduce_min_sync(0xffffffffu, (unsigned)cx);
@@ -1457,11 +1231,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                                            box.hix, box.hiy, box.hiz, cx, cy, lz, gz, cx_min, cx_max, lst, lst_j,
                                            share, rows_per_share, part);
         h.ax = f.x; h.ay = f.y; h.az = f.z;
-#ifndef GOF_NO_GROUP_WALK
-    } else if (as_warp && SPLIT > 1) {
-#else
     } else if (as_warp) {
-#endif
         const Box box = warp_box(h);
         const int cx_min = (int)__reduce_min_sync(0xffffffffu, (unsigned)cx);
         const int cx_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)cx);
@@ -1654,9 +1424,9 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
 // ---- diagnostics (bench.py): how much of the neighbour search is useful work --------------------
 // For the snapshot the last force launch read, per home particle:
 //   candidates  population of its 9 / 27 stencil cells (what a plain cell-list walk would test)
-//   evaluated   force evaluations the Clusters kernel spends on it: the survivors of its group's
-//               box test, every run padded to a multiple of four (walk_groups); lanes on the other
-//               paths (a group that straddles two rows of cells, the literal z-wrap layers) and the
+//   evaluated   force evaluations the Clusters kernel spends on it: the survivors of its warp's
+//               box test, every run padded to a multiple of four (walk_culled); lanes on the other
+//               paths (a warp that straddles two rows of cells, the literal z-wrap layers) and the
 //               Boids / mixed kernels test every candidate
 //   in_range    candidates closer than r_max (fp32, periodic image of the run; no float64 repair)
 // Summed over the particles with one atomic per warp.  Not part of a step; never timed.
@@ -1684,22 +1454,11 @@ k_pair_stats(const __grid_constant__ Geometry g, const float4* __restrict__ posw
                              (double)(rp + 1) * g.bsy > band;
         if (!in_band) { quirk = false; skip_dz = gz == 0 ? -1 : 1; }
     }
-    float blox = h.x, bhix = h.x, bloy = h.y, bhiy = h.y, bloz = h.z, bhiz = h.z;
-    int cxl = cx, cxh = cx, rlo = cyz, rhi = cyz;
-#pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
-        blox = fminf(blox, __shfl_xor_sync(0xffffffffu, blox, d));
-        bhix = fmaxf(bhix, __shfl_xor_sync(0xffffffffu, bhix, d));
-        bloy = fminf(bloy, __shfl_xor_sync(0xffffffffu, bloy, d));
-        bhiy = fmaxf(bhiy, __shfl_xor_sync(0xffffffffu, bhiy, d));
-        bloz = fminf(bloz, __shfl_xor_sync(0xffffffffu, bloz, d));
-        bhiz = fmaxf(bhiz, __shfl_xor_sync(0xffffffffu, bhiz, d));
-        cxl = min(cxl, __shfl_xor_sync(0xffffffffu, cxl, d));
-        cxh = max(cxh, __shfl_xor_sync(0xffffffffu, cxh, d));
-        rlo = min(rlo, __shfl_xor_sync(0xffffffffu, rlo, d));
-        rhi = max(rhi, __shfl_xor_sync(0xffffffffu, rhi, d));
-    }
-    const bool as_groups = clusters && __all_sync(0xffffffffu, rlo == rhi && !quirk);
+    // (every lane takes part in the reductions: no short-circuit in front of them)
+    const Box b = warp_box(h);
+    const int cxl = (int)__reduce_min_sync(0xffffffffu, (unsigned)cx), cxh = (int)__reduce_max_sync(0xffffffffu, (unsigned)cx);
+    const bool one_row = __reduce_min_sync(0xffffffffu, (unsigned)cyz) == __reduce_max_sync(0xffffffffu, (unsigned)cyz);
+    const bool as_warp = clusters && one_row && __all_sync(0xffffffffu, !quirk);
     unsigned long long cand = 0, eval = 0, inr = 0;
     const int nrows = g.is3d ? 9 : 3;
     for (int r = 0; r < nrows; ++r) {
@@ -1718,20 +1477,20 @@ k_pair_stats(const __grid_constant__ Geometry g, const float4* __restrict__ posw
         for (int part = 0; part < 3; ++part) {
             // own run of this lane (part 0: cells cx - 1 .. cx + 1; 1 / 2: the cell across the x edge)
             int s, e, sx = 0;
-            int gs, ge;  // the group's run
+            int ws, we;  // the warp's run
             if (part == 0) {
                 const int lo = cx > 0 ? cx - 1 : 0, hi = cx < g.nbx - 1 ? cx + 1 : g.nbx - 1;
                 s = start[rb + lo]; e = start[rb + hi] + count[rb + hi];
-                const int glo = cxl > 0 ? cxl - 1 : 0, ghi = cxh < g.nbx - 1 ? cxh + 1 : g.nbx - 1;
-                gs = start[rb + glo]; ge = start[rb + ghi] + count[rb + ghi];
+                const int wlo = cxl > 0 ? cxl - 1 : 0, whi = cxh < g.nbx - 1 ? cxh + 1 : g.nbx - 1;
+                ws = start[rb + wlo]; we = start[rb + whi] + count[rb + whi];
             } else if (part == 1) {
                 sx = 1;
                 s = start[rb + g.nbx - 1]; e = cx == 0 ? s + count[rb + g.nbx - 1] : s;
-                gs = s; ge = cxl == 0 ? s + count[rb + g.nbx - 1] : s;
+                ws = s; we = cxl == 0 ? s + count[rb + g.nbx - 1] : s;
             } else {
                 sx = -1;
                 s = start[rb]; e = cx == g.nbx - 1 ? s + count[rb] : s;
-                gs = s; ge = cxh == g.nbx - 1 ? s + count[rb] : s;
+                ws = s; we = cxh == g.nbx - 1 ? s + count[rb] : s;
             }
             cand += (unsigned long long)(e - s);
             const Image im = make_image(h, g, sx, sy, sz);
@@ -1741,13 +1500,13 @@ k_pair_stats(const __grid_constant__ Geometry g, const float4* __restrict__ posw
                 const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 inr += (d2 < g.r2_lo && d2 > 1e-10f) ? 1u : 0u;
             }
-            if (as_groups) {
+            if (as_warp) {
                 const float tx = sx * g.Lx, ty = sy * g.Ly, tz = sz * g.Lz;
-                const float lox = blox + tx - g.cull_slack, hix = bhix + tx + g.cull_slack;
-                const float loy = bloy + ty - g.cull_slack, hiy = bhiy + ty + g.cull_slack;
-                const float loz = bloz + tz - g.cull_slack, hiz = bhiz + tz + g.cull_slack;
+                const float lox = b.lox + tx - g.cull_slack, hix = b.hix + tx + g.cull_slack;
+                const float loy = b.loy + ty - g.cull_slack, hiy = b.hiy + ty + g.cull_slack;
+                const float loz = b.loz + tz - g.cull_slack, hiz = b.hiz + tz + g.cull_slack;
                 unsigned kept = 0;
-                for (int j = gs; j < ge; ++j) {
+                for (int j = ws; j < we; ++j) {
                     const float4 p = ldg4(posw + j);
                     const float ex = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
                     const float ey = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
