@@ -8,7 +8,16 @@ One "step" is one Simulation.core_step (bin -> neighbour forces -> integrate)
 over the synthetic workload named in `config.workload`.  At N=1 that is
 BASELINE.json configs[1]: Clusters 3D, 5 species, N = 1,000,000, periodic box,
 at the number density of the reference's own 3D run (hive.py: 14,000 particles
-in 100^3 = 0.014 / unit^3), uniform random start, adaptive timestep.
+in 100^3 = 0.014 / unit^3), uniform random start, adaptive timestep.  At N>1 the
+box of the one-GPU workload is stacked N times along z and cut into N z-slabs
+(weak scaling, one slab per GPU).
+
+Both arms (`--impl b200`, `--impl reference`) build the SAME initial state with
+`global_state()`: the reference arm runs the oracle port (oracle/gof_oracle.c,
+the reference's algorithm restated in C: half stencil + atomics, float64,
+OpenMP over particles like numba-parallel) on ALL host cores this process may
+use (`os.sched_getaffinity`, whatever OMP_NUM_THREADS says: torchrun sets it to
+1) at the same N as the GPU arm, unless that would not fit the time budget.
 
 Prints ONE JSON line (rank 0).  See the module constants for the algorithmic
 byte count behind `roofline`.
@@ -46,6 +55,15 @@ WORKLOADS = {
 }
 
 
+def host_threads() -> int:
+    """Cores this process may run on.  Not omp_get_max_threads(): torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which would time the host baseline on one core."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 def build_workload(name: str, n_particles: int, seed: int, density: float | None):
     """Initial state through the package's own host constructor logic (same code path as
     Simulation.__init__), on a cubic / square box sized for the reference density."""
@@ -72,6 +90,48 @@ def build_workload(name: str, n_particles: int, seed: int, density: float | None
         hs = host_state(counts[:h], counts[h:], seed=seed, limits=limits)
     hs["density"] = rho
     hs["box"] = limits
+    return hs
+
+
+def slab_particles(args, side: float, bin_size_z: float, lo: int, hi: int, rank: int, n: int, species: int):
+    """Rank `rank`'s particles of the multi-GPU workload: n particles uniform in its slab of
+    z-layers [lo, hi), types round-robin blocks, global ids rank * n + i."""
+    rng = np.random.default_rng(args.seed + rank)
+    pos = rng.random((3, n))
+    pos[0] *= side
+    pos[1] *= side
+    pos[2] = (lo + pos[2] * (hi - lo)) * bin_size_z
+    pos = pos.astype(np.float32)
+    types = np.repeat(np.arange(species, dtype=np.int32), -(-n // species))[:n]
+    ids = np.arange(n, dtype=np.int32) + rank * n
+    return pos, types, ids
+
+
+def global_state(args, world: int, n: int):
+    """The whole job's species, box and (lazily) particles, identical for both arms.
+
+    world == 1: the workload as Simulation.__init__ would build it.  world > 1: the one-GPU box
+    stacked `world` times along z, cut into `world` slabs of whole bin layers."""
+    from game_of_flies_b200 import _lib
+    from game_of_flies_b200.slab import split_layers
+    if world == 1:
+        hs = build_workload(args.workload, n, args.seed, args.density)
+        hs["layers"] = None
+        return hs
+    kind, species, dims = WORKLOADS[args.workload]
+    if dims != 3:
+        raise SystemExit("the slab decomposition needs a 3D workload")
+    hs = build_workload(args.workload, 1000, args.seed, args.density)  # species parameters only
+    rho = hs["density"]
+    side = float((n / rho) ** (1.0 / 3.0))
+    limits = np.array([side, side, side * world])
+    hs["limits"], hs["box"] = limits, tuple(limits)
+    grid = _lib.make_grid(limits, float(hs["r_max"]))
+    hs["num_bin_x"], hs["num_bin_y"], hs["num_bin_z"] = grid.num_bin_x, grid.num_bin_y, grid.num_bin_z
+    hs["grid"] = grid
+    hs["side"] = side
+    hs["layers"] = split_layers(int(grid.num_bin_z), world)
+    hs["species"] = species
     return hs
 
 
@@ -155,30 +215,28 @@ def recorded_capture(workload: str, n: int):
     return None
 
 
-def recorded_traffic(workload: str, n: int):
-    """dram bytes per force-kernel launch from the committed ncu capture, if one matches."""
-    r = recorded_capture(workload, n)
-    return float(r["dram_bytes_per_launch"]) if r else None
-
-
-def oracle_sim_from(hs, n_threads):
+def oracle_sim_from(hs, n_threads, pos=None, types=None):
     from oracle import oracle as orc
-    init = hs["init"]
     f = lambda *a: np.stack(a).astype(np.float32).astype(np.float64)
-    return orc.OracleSimulation(f(init["pos_x"], init["pos_y"], init["pos_z"]),
-                                f(init["vel_x"], init["vel_y"], init["vel_z"]),
-                                f(init["acc_x"], init["acc_y"], init["acc_z"]),
-                                hs["particle_type_index_array"], hs["parameter_matrix"],
-                                hs["limits"], float(hs["r_max"]), timestep=None, n_threads=n_threads)
+    if pos is None:
+        init = hs["init"]
+        p = f(init["pos_x"], init["pos_y"], init["pos_z"])
+        v = f(init["vel_x"], init["vel_y"], init["vel_z"])
+        a = f(init["acc_x"], init["acc_y"], init["acc_z"])
+        types = hs["particle_type_index_array"]
+    else:
+        p = np.ascontiguousarray(pos, dtype=np.float64)
+        v = np.zeros_like(p)
+        a = np.zeros_like(p)
+    return orc.OracleSimulation(p, v, a, types, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]),
+                                timestep=None, n_threads=n_threads)
 
 
 def cpu_baseline(workload: str, seed: int, density, budget_s: float = 20.0):
-    """The oracle port (reference algorithm: half stencil + atomics, float64, OpenMP over
-    particles like numba-parallel) on this host's cores, on a bounded sample of the workload:
-    the same species, parameters, density and box shape at a particle count that one step
-    finishes in seconds.  particle-updates/s is intensive at fixed density."""
-    from oracle import oracle as orc
-    threads = orc.max_threads()
+    """The oracle port on this host's cores, on a bounded sample of the workload: the same species,
+    parameters, density and box shape at a particle count that one step finishes in seconds.
+    particle-updates/s is intensive at fixed density."""
+    threads = host_threads()
     n_sample = 250_000
     hs = build_workload(workload, n_sample, seed, density)
     o = oracle_sim_from(hs, threads)
@@ -198,47 +256,78 @@ def cpu_baseline(workload: str, seed: int, density, budget_s: float = 20.0):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's algorithm on the host cores (oracle port; the
-    reference itself is numba-CUDA Python and cannot be compiled into oracle/_ref)."""
+    """--impl reference: the reference's algorithm on the host cores (oracle port: the reference
+    itself is numba-CUDA Python and cannot be compiled into oracle/_ref; its own GPU kernels are
+    timed on the same box by baseline/run_reference_gpu.py, see profiles/).  Same initial state as
+    the GPU arm (`global_state`), all host threads; under torchrun rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
-    threads = orc.max_threads()
-    n_sample = args.reference_particles
-    hs = build_workload(args.workload, n_sample, args.seed, args.density)
-    o = oracle_sim_from(hs, threads)
+    world = max(int(os.environ.get("WORLD_SIZE", str(args.gpus))), 1)
+    threads = host_threads()
+    n_total = world * args.particles
+    budget_s = args.reference_seconds
+    # Same N as the GPU arm unless (warmup + steps) of it cannot fit the budget: a short probe at
+    # N = 100k measures this host's rate (particle-updates/s is intensive at fixed density).
+    probe = build_workload(args.workload, 100_000, args.seed, args.density)
+    o = oracle_sim_from(probe, threads)
+    o.core_step()
+    t0 = time.perf_counter()
+    o.core_step()
+    rate = 100_000 / (time.perf_counter() - t0)
+    fits = n_total * (args.steps + args.warmup) / rate <= budget_s
+    if args.reference_particles:
+        n_run, same = int(args.reference_particles), int(args.reference_particles) == n_total
+    elif fits:
+        n_run, same = n_total, True
+    else:
+        n_run = int(max(100_000, budget_s * rate / (args.steps + args.warmup)))
+        same = False
+    if same and world > 1:
+        hs = global_state(args, world, args.particles)
+        parts = [slab_particles(args, hs["side"], float(hs["grid"].bin_size_z), lo, hi, r, args.particles, hs["species"])
+                 for r, (lo, hi) in enumerate(hs["layers"])]
+        pos = np.concatenate([p[0] for p in parts], axis=1)
+        types = np.concatenate([p[1] for p in parts])
+        o = oracle_sim_from(hs, threads, pos=pos, types=types)
+    else:
+        hs = build_workload(args.workload, n_run, args.seed, args.density)
+        o = oracle_sim_from(hs, threads)
     for _ in range(args.warmup):
         o.core_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         o.core_step()
     el = time.perf_counter() - t0
-    value = n_sample * args.steps / el
+    value = n_run * args.steps / el
+    sample = (f"{args.steps} steps at N={n_run}" + (" (the GPU arm's N and initial state)" if same else
+              f" (bounded sample: the GPU arm's N={n_total} would need more than {budget_s:.0f} s; same "
+              "density, species and parameters)") + f", {threads} OpenMP threads")
     line = {
-        "impl": "reference",
+        "impl": "reference", "reference_kind": "oracle port of the reference algorithm on host cores (C, OpenMP)",
         "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, hs, n_sample, note="bounded sample of the workload on host cores"),
+        "config": workload_config(args, hs, n_run, world=world if same else 1,
+                                  note=None if same else "bounded sample of the workload on host cores"),
+        "same_config": same,
         "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps at N={n_sample}, same density/species/parameters as the "
-                                   f"GPU arm's workload, {threads} OpenMP threads"},
+                         "sample": sample},
         "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, hs, n_total, note=None):
+def workload_config(args, hs, n_total, world=1, note=None):
     kind, species, dims = WORKLOADS[args.workload]
     cfg = {
         "workload": f"{kind.capitalize()} {dims}D, {species} species, N={n_total}, periodic box "
                     f"{tuple(round(float(x), 2) for x in hs['box'])}, density {hs['density']:.4g}, "
                     f"r_max {float(hs['r_max']):.3f}, uniform random start, "
                     + ("adaptive timestep" if args.timestep is None else f"fixed timestep {args.timestep}"),
-        "particles_per_gpu": int(n_total // max(int(os.environ.get("WORLD_SIZE", "1")), 1)),
+        "particles_per_gpu": int(n_total // max(world, 1)),
         "bins": [int(hs["num_bin_x"]), int(hs["num_bin_y"]), int(hs["num_bin_z"])],
         "wrap_mode": getattr(args, "wrap", "reference"),
         "cache": ("L2 flushed between timed steps (256 MiB overwrite outside the per-step event pairs)"
@@ -249,6 +338,67 @@ def workload_config(args, hs, n_total, note=None):
     return cfg
 
 
+def slab_parity_check(args, world, rank, device, wrap_mode, make_runner):
+    """Multi-process self-check before any timing: a 100k-particle box of the same species runs 6
+    adaptive steps on the slab path (this job's transport, one slab per rank) and on ONE engine on
+    rank 0; positions, velocities and accelerations must agree bit for bit, particle by particle."""
+    import torch
+    import torch.distributed as dist
+    from game_of_flies_b200 import _lib
+    from game_of_flies_b200.engine import ParticleEngine
+    from game_of_flies_b200.slab import SlabEngine, assign_to_slabs, split_layers
+    kind, species, dims = WORKLOADS[args.workload]
+    hs = build_workload(args.workload, 1000, args.seed, args.density)
+    r_max, rho = float(hs["r_max"]), float(hs["density"])
+    n_total, steps = 100_000, 6
+    side = 8.5 * r_max
+    lz = max(n_total / (rho * side * side), (2 * world + 0.5) * r_max)
+    limits = np.array([side, side, lz])
+    grid = _lib.make_grid(limits, r_max)
+    layers = split_layers(int(grid.num_bin_z), world)
+    rng = np.random.default_rng(args.seed + 1000)
+    pos = (rng.random((3, n_total)) * limits[:, None]).astype(np.float32)
+    vel = rng.normal(0.0, 3.0, (3, n_total)).astype(np.float32)
+    acc = np.zeros((3, n_total), dtype=np.float32)
+    types = (np.arange(n_total) % species).astype(np.int32)
+    owner = assign_to_slabs(pos[2], float(grid.bin_size_z), int(grid.num_bin_z), layers)
+    m = owner == rank
+    lo, hi = layers[rank]
+    eng = SlabEngine(hs["parameter_matrix"], limits, r_max, lo, hi, capacity=int(m.sum() * 1.5) + 8192,
+                     device=device, wrap_mode=wrap_mode)
+    eng.upload(pos[:, m], types[m], np.nonzero(m)[0].astype(np.int32), vel=vel[:, m], acc=acc[:, m])
+    runner = make_runner(eng)
+    runner.step(steps, None)
+    d = eng.download()
+    bits = torch.zeros((9, n_total), dtype=torch.int32, device=device)
+    own = torch.zeros(n_total, dtype=torch.int32, device=device)
+    ids = torch.from_numpy(d["ids"].astype(np.int64)).to(device)
+    stack = np.concatenate([d["pos"], d["vel"], d["acc"]]).view(np.int32)
+    bits[:, ids] = torch.from_numpy(stack).to(device)
+    own[ids] = 1
+    dist.all_reduce(bits)
+    dist.all_reduce(own)
+    runner.close()
+    eng.close()
+    res = None
+    if rank == 0:
+        single = ParticleEngine(n_total, hs["parameter_matrix"], limits, r_max, device=device, wrap_mode=wrap_mode)
+        single.upload([pos[k] for k in range(3)], types, vel=[vel[k] for k in range(3)], acc=[acc[k] for k in range(3)])
+        single.step(steps, None)
+        w = single.download(pos=True, vel=True, acc=True)
+        single.close()
+        want = np.concatenate([w["pos"], w["vel"], w["acc"]]).view(np.int32)
+        got = bits.cpu().numpy()
+        owned_once = bool((own.cpu().numpy() == 1).all())
+        moved = int((assign_to_slabs(w["pos"][2], float(grid.bin_size_z), int(grid.num_bin_z), layers) != owner).sum())
+        res = {"bit_identical": bool(owned_once and np.array_equal(got, want)), "n": n_total, "steps": steps,
+               "slabs": world, "every_particle_owned_once": owned_once, "migrated": moved,
+               "against": "one engine on rank 0, same initial state"}
+    flag = torch.tensor([1 if (res is None or res["bit_identical"]) else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,15 +407,24 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="clusters3d", choices=sorted(WORKLOADS))
     ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU")
-    ap.add_argument("--reference-particles", type=int, default=100_000)
+    ap.add_argument("--reference-particles", type=int, default=0,
+                    help="force the reference arm's N (default: the GPU arm's N when it fits --reference-seconds)")
+    ap.add_argument("--reference-seconds", type=float, default=150.0)
     ap.add_argument("--density", type=float, default=None)
     ap.add_argument("--seed", type=int, default=434)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--evolve", type=int, default=300,
+                    help="steps to evolve before the steady-state timing (0: skip it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true",
+                    help="at 8 GPUs, skip the second timed configuration (3D Clusters N=16M)")
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false",
                     help="do not overwrite a 256 MiB buffer between timed steps")
     ap.add_argument("--wrap", default="reference", choices=["reference", "minimage"],
                     help="periodic wrap semantics: the reference's (z-wrap quirk included) or minimum image")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU halo / migration transport: peer-memory stores or NCCL send/recv")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--timestep", type=float, default=None,
                     help="fixed timestep (default: the reference's adaptive one, 0.4 / max speed)")
@@ -299,179 +458,229 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     lib = _lib.load()
     _lib.check(lib.gof_set_force_split(args.force_split))
-    n = args.particles
-    cand = None
     wrap_mode = _lib.WRAP_REFERENCE if args.wrap == "reference" else _lib.WRAP_MINIMAGE
-    if world == 1:
-        # ---- one GPU: the resident engine on the whole periodic box -------------------------
-        hs = build_workload(args.workload, n, args.seed, args.density)
-        init = hs["init"]
-        pin = lambda a, dt=np.float32: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory()
-        h_pos = [pin(init[k]) for k in ("pos_x", "pos_y", "pos_z")]
-        h_vel = [pin(init[k]) for k in ("vel_x", "vel_y", "vel_z")]
-        h_acc = [pin(init[k]) for k in ("acc_x", "acc_y", "acc_z")]
-        h_types = pin(hs["particle_type_index_array"], np.int32)
-        o_pos = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
-        o_vel = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
-        o_acc = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
-        eng = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), device=device,
-                             wrap_mode=wrap_mode)
-        eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
-        step = lambda k: eng.step(k, args.timestep)
+    pin = lambda a, dt=np.float32: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory()
+    parity = None
 
-        def e2e_step():
-            nonlocal h_pos, h_vel, h_acc, o_pos, o_vel, o_acc
+    def make_job(n):
+        """Engine, step(k) and e2e_step() for `n` particles per GPU."""
+        hs = global_state(args, world, n)
+        if world == 1:
+            # ---- one GPU: the resident engine on the whole periodic box ---------------------
+            init = hs["init"]
+            h_pos = [pin(init[k]) for k in ("pos_x", "pos_y", "pos_z")]
+            h_vel = [pin(init[k]) for k in ("vel_x", "vel_y", "vel_z")]
+            h_acc = [pin(init[k]) for k in ("acc_x", "acc_y", "acc_z")]
+            h_types = pin(hs["particle_type_index_array"], np.int32)
+            bufs = {"in": (h_pos, h_vel, h_acc),
+                    "out": tuple([torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)] for _ in range(3))}
+            eng = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), device=device,
+                                 wrap_mode=wrap_mode)
             eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
-            eng.step(1, args.timestep)
-            eng.download_into(pos=o_pos, vel=o_vel, acc=o_acc)
-            torch.cuda.current_stream(device).synchronize()
-            # the next step of a host-driven loop starts from what came back
-            h_pos, o_pos = o_pos, h_pos
-            h_vel, o_vel = o_vel, h_vel
-            h_acc, o_acc = o_acc, h_acc
-    else:
-        # ---- several GPUs: z-slab decomposition, one slab per rank, weak scaling -----------------
-        # the box of the one-GPU workload stacked `world` times along z; every rank starts with
-        # `n` particles uniform in its own slab
-        from game_of_flies_b200.slab import DistComm, SlabEngine, SlabRunner, split_layers
-        hs = build_workload(args.workload, 1000, args.seed, args.density)  # species parameters only
-        kind, species, dims = WORKLOADS[args.workload]
-        if dims != 3:
-            raise SystemExit("the slab decomposition needs a 3D workload")
-        rho = hs["density"]
-        side = float((n / rho) ** (1.0 / 3.0))
-        limits = np.array([side, side, side * world])
-        hs["limits"], hs["box"] = limits, tuple(limits)
-        grid = _lib.make_grid(limits, float(hs["r_max"]))
-        hs["num_bin_x"], hs["num_bin_y"], hs["num_bin_z"] = grid.num_bin_x, grid.num_bin_y, grid.num_bin_z
-        layers = split_layers(int(grid.num_bin_z), world)
-        lo, hi = layers[rank]
-        rng = np.random.default_rng(args.seed + rank)
-        pos = rng.random((3, n))
-        pos[0] *= side
-        pos[1] *= side
-        pos[2] = (lo + pos[2] * (hi - lo)) * grid.bin_size_z
-        pos = pos.astype(np.float32)
-        types = np.repeat(np.arange(species, dtype=np.int32), -(-n // species))[:n]
-        ids = np.arange(n, dtype=np.int32) + rank * n
-        zeros = np.zeros((3, n), dtype=np.float32)
-        eng = SlabEngine(hs["parameter_matrix"], limits, float(hs["r_max"]), lo, hi, capacity=int(1.3 * n) + 8192,
+            step = lambda k: eng.step(k, args.timestep)
+
+            def e2e_step():
+                p, v, a = bufs["in"]
+                eng.upload(p, h_types, vel=v, acc=a)
+                eng.step(1, args.timestep)
+                op, ov, oa = bufs["out"]
+                eng.download_into(pos=op, vel=ov, acc=oa)
+                torch.cuda.current_stream(device).synchronize()
+                # the next step of a host-driven loop starts from what came back
+                bufs["in"], bufs["out"] = bufs["out"], bufs["in"]
+            return hs, eng, None, step, e2e_step
+        # ---- several GPUs: z-slab decomposition, one slab per rank, weak scaling ---------------
+        from game_of_flies_b200.slab import SlabEngine, make_runner
+        lo, hi = hs["layers"][rank]
+        pos, types, ids = slab_particles(args, hs["side"], float(hs["grid"].bin_size_z), lo, hi, rank, n,
+                                         hs["species"])
+        cap = int(1.3 * n) + 8192
+        eng = SlabEngine(hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), lo, hi, capacity=cap,
                          device=device, wrap_mode=wrap_mode)
+        zeros = np.zeros((3, n), dtype=np.float32)
         eng.upload(pos, types, ids, vel=zeros, acc=zeros)
-        runner = SlabRunner({rank: eng}, world, DistComm(world, device=device))
+        runner = make_runner(eng, world, device, transport=args.transport)
         step = lambda k: runner.step(k, args.timestep)
-        state = {"pos": pos, "vel": zeros, "acc": zeros, "types": types, "ids": ids}
+        # end to end: pinned, preallocated host buffers of `capacity` entries, ping-pong like the
+        # one-GPU path; the particle count of a slab changes from step to step (migration)
+        mk = lambda dt=torch.float32: torch.empty(cap, dtype=dt).pin_memory()
+        host = [dict(pos=[mk() for _ in range(3)], vel=[mk() for _ in range(3)], acc=[mk() for _ in range(3)],
+                     types=mk(torch.int32), ids=mk(torch.int32), n=0) for _ in range(2)]
+        for k in range(3):
+            host[0]["pos"][k][:n] = torch.from_numpy(pos[k])
+            host[0]["vel"][k][:n] = 0
+            host[0]["acc"][k][:n] = 0
+        host[0]["types"][:n] = torch.from_numpy(types)
+        host[0]["ids"][:n] = torch.from_numpy(ids)
+        host[0]["n"] = n
+        cur = [0]
 
         def e2e_step():
-            eng.upload(state["pos"], state["types"], state["ids"], vel=state["vel"], acc=state["acc"])
+            a, b = host[cur[0]], host[cur[0] ^ 1]
+            eng.upload(a["pos"], a["types"], a["ids"], vel=a["vel"], acc=a["acc"], n=a["n"])
             runner.step(1, args.timestep)
-            d = eng.download()
-            state["pos"], state["vel"], state["acc"], state["ids"] = d["pos"], d["vel"], d["acc"], d["ids"]
-            # types travel with the particles: recover them from the ids (species are id ranges per rank)
-            state["types"] = types[(d["ids"] % n)]
+            b["n"] = eng.download_into(b["pos"], b["vel"], b["acc"], b["ids"], b["types"])
+            cur[0] ^= 1
+        return hs, eng, runner, step, e2e_step
 
-    # ---- device-resident throughput ------------------------------------------------------------
-    step(args.warmup)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    eng.timing(True)
-    lib.gof_reset_launch_count()
-    # Every timed step starts with a cold L2: a 256 MiB buffer (2x the 126 MB L2) is overwritten
-    # between steps, outside the per-step event pairs, because the per-step working set at
-    # N = 1M (~100 MB) would otherwise stay L2-resident from one step to the next.
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if args.flush_l2 else None
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
-        if flush is not None:
-            flush.fill_(k & 0xFF)
-        starts[k].record()
-        step(1)
-        stops[k].record()
-    barrier()
-    launches = int(lib.gof_launch_count())
-    ms_total = float(sum(a.elapsed_time(b) for a, b in zip(starts, stops)))
-    force_ms, force_launches = eng.force_time()
-    eng.timing(False)
-    clocks = sampler.stop()
-    if world == 1:
-        cand = eng.candidate_pairs()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = world * n * args.steps / (ms_total * 1e-3)
+    if world > 1 and not args.no_parity_check:
+        from game_of_flies_b200.slab import make_runner
+        parity = slab_parity_check(args, world, rank, device, wrap_mode,
+                                   lambda e: make_runner(e, world, device, transport=args.transport))
 
-    # ---- end to end through the public API with host buffers ------------------------------
-    # every step: host state -> device, one core_step, full state back to the host
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = world * n * args.e2e_steps / e2e_s
-    h2d = n * (9 * 4 + 4) + (n * 4 if world > 1 else 0)
-    d2h = n * 9 * 4 + (n * 4 if world > 1 else 0)
+    def timed_run(n, steps, warmup, e2e_steps, evolve):
+        hs, eng, runner, step, e2e_step = make_job(n)
+        step(warmup)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        eng.timing(True)
+        lib.gof_reset_launch_count()
+        # Every timed step starts with a cold L2: a 256 MiB buffer (2x the 126 MB L2) is overwritten
+        # between steps, outside the per-step event pairs, because the per-step working set at
+        # N = 1M (~100 MB) would otherwise stay L2-resident from one step to the next.
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if args.flush_l2 else None
 
-    if world > 1 and rank == 0 and getattr(runner, "phase_ms", None):
-        pm = runner.phase_ms
-        print(f"[slab timing] per step: prefix (hash, migration, sort) {pm['prefix'] / max(pm['steps'], 1):.4f} ms, "
-              f"forces + halo {pm['forces'] / max(pm['steps'], 1):.4f} ms", file=sys.stderr, flush=True)
+        def timed_steps(count):
+            starts = [torch.cuda.Event(enable_timing=True) for _ in range(count)]
+            stops = [torch.cuda.Event(enable_timing=True) for _ in range(count)]
+            barrier()
+            for k in range(count):
+                if flush is not None:
+                    flush.fill_(k & 0xFF)
+                starts[k].record()
+                step(1)
+                stops[k].record()
+            barrier()
+            return max_over_ranks(float(sum(a.elapsed_time(b) for a, b in zip(starts, stops))))
+
+        ms_total = timed_steps(steps)
+        launches = int(lib.gof_launch_count())
+        force_ms, force_launches = eng.force_time()
+        eng.timing(False)
+        clocks = sampler.stop()
+        stats = eng.pair_stats() if hasattr(eng, "pair_stats") else None
+        out = {"hs": hs, "ms_total": ms_total, "launches": launches, "force_ms": force_ms,
+               "force_launches": force_launches, "clocks": clocks, "stats": stats,
+               "value": world * n * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps}
+        # ---- end to end through the public API with host buffers --------------------------
+        # every step: host state -> device, one core_step, full state back to the host
+        if e2e_steps > 0:
+            e2e_step()  # (first call touches the pinned buffers)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            barrier()
+            e2e_s = max_over_ranks(time.perf_counter() - t0)
+            out["e2e_value"] = world * n * e2e_steps / e2e_s
+        # ---- steady state: the same system after it has clumped ---------------------------
+        if evolve > 0:
+            # (the end-to-end steps above left the state `e2e_steps` further on; the count below is
+            # what matters: clusters have formed after ~150 steps)
+            step(evolve)
+            ms_ss = timed_steps(steps)
+            st2 = eng.pair_stats() if hasattr(eng, "pair_stats") else None
+            out["steady"] = {"evolve_steps": evolve, "value": world * n * steps / (ms_ss * 1e-3),
+                             "ms_per_step": ms_ss / steps, "unit": "particle-updates/s",
+                             "what": f"the same run timed again after {evolve} more steps (particles clumped)"}
+            if st2:
+                out["steady"].update({"pairs_in_range_per_particle": st2["in_range"] / max(st2["n"], 1),
+                                      "pairs_evaluated_per_particle": st2["evaluated"] / max(st2["n"], 1)})
+        if runner is not None and rank == 0 and getattr(runner, "phase_ms", None):
+            pm = runner.phase_ms
+            print(f"[slab timing] per step: prefix (hash, migration, sort) {pm['prefix'] / max(pm['steps'], 1):.4f} ms, "
+                  f"forces + halo {pm['forces'] / max(pm['steps'], 1):.4f} ms", file=sys.stderr, flush=True)
+        out["transport"] = getattr(runner, "transport", None)
+        if runner is not None:
+            runner.close()
+        eng.close()
+        return out
+
+    n = args.particles
+    res = timed_run(n, args.steps, args.warmup, args.e2e_steps, args.evolve if world == 1 else 0)
+    north = None
+    if world == 8 and args.workload == "clusters3d" and n != 2_000_000 and not args.no_north_star:
+        # BASELINE.json's target configuration, as a second timed run of the same job
+        r2 = timed_run(2_000_000, args.steps, args.warmup, 0, 0)
+        north = {"workload": "Clusters 3D, 5 species, N=16000000 on 8 GPUs (2M per GPU)", "value": r2["value"],
+                 "unit": "particle-updates/s", "ms_per_step": r2["ms_per_step"], "steps": args.steps,
+                 "target": 1.0e10, "clocks": r2["clocks"]}
+
     if rank == 0:
+        hs = res["hs"]
         peak, peak_src = measured_peaks()
-        force_avg_ms = force_ms / max(force_launches, 1)
-        achieved = FORCE_BYTES_PER_PARTICLE * n / (force_avg_ms * 1e-3) / 1e9
+        steps = args.steps
+        # force-kernel time PER STEP: one launch on one GPU; interior + boundary launches in slab mode
+        # (they overlap on two streams, so their sum can exceed the step's wall time)
+        force_ms_step = res["force_ms"] / steps
+        achieved = FORCE_BYTES_PER_PARTICLE * n / (force_ms_step * 1e-3) / 1e9
+        cap = recorded_capture(args.workload, n) if world == 1 else None
+        stats = res["stats"]
         roofline = {
             "bound": "hbm",
             "kernel": "gof::k_force<%s, integrate> (neighbour force + integrator)"
                       % {"clusters": "Clusters", "boids": "Boids", "mixed": "Mixed"}[WORKLOADS[args.workload][0]],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_src,
-            "traffic": recorded_traffic(args.workload, n),
-            # the kernel's real limit, from the same ncu capture (profiles/): issue slots in use
-            "issue_active_pct": (recorded_capture(args.workload, n) or {}).get("issue_active_pct"),
-            "active_lanes": (recorded_capture(args.workload, n) or {}).get("active_lanes_per_instruction"),
-            "algorithmic_bytes_per_launch": FORCE_BYTES_PER_PARTICLE * n,
-            "avg_launch_ms": force_avg_ms, "launches_timed": force_launches,
-            "share_of_step": force_ms / ms_total if ms_total > 0 else None,
-            # why the HBM fraction is what it is: the kernel is instruction-issue bound on the
-            # neighbour search (stencil candidates = population of a particle's 9 / 27 cells; the
-            # Clusters kernel culls about 45 % of them per warp before evaluating)
-            "candidate_pairs_per_particle": (cand / n) if cand is not None else None,
-            "stencil_candidates_per_s": (cand / (force_avg_ms * 1e-3)) if cand is not None else None,
+            "traffic": float(cap["dram_bytes_per_launch"]) if cap else None,
+            "traffic_source": "committed ncu capture of this workload (profiles/force_kernel_traffic.json), "
+                              "not measured in this run" if cap else None,
+            "algorithmic_bytes_per_step": FORCE_BYTES_PER_PARTICLE * n,
+            "force_ms_per_step": force_ms_step, "launches_timed": res["force_launches"],
+            "launches_per_step": res["force_launches"] / steps,
+            "share_of_step": res["force_ms"] / res["ms_total"] if res["ms_total"] > 0 else None,
         }
+        if cap:
+            roofline["recorded_issue_active_pct"] = cap.get("issue_active_pct")
+            roofline["recorded_active_lanes"] = cap.get("active_lanes_per_instruction")
+        if stats:
+            # why the HBM fraction is what it is: the kernel is instruction-issue bound on the
+            # neighbour search.  Per particle: stencil candidates (population of its 9 / 27 cells),
+            # candidates the kernel evaluates after culling, and pairs really in range.
+            roofline.update({
+                "candidates_per_particle": stats["candidates"] / stats["n"],
+                "pairs_evaluated_per_particle": stats["evaluated"] / stats["n"],
+                "pairs_in_range_per_particle": stats["in_range"] / stats["n"],
+                "evaluated_per_in_range": stats["evaluated"] / max(stats["in_range"], 1),
+                "pairs_evaluated_per_s": stats["evaluated"] / (force_ms_step * 1e-3),
+            })
+        h2d = n * (9 * 4 + 4) + (n * 4 if world > 1 else 0)
+        d2h = n * 9 * 4 + (n * 8 if world > 1 else 0)
         line = {
-            "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "metric": "particle-updates/sec", "value": res["value"], "unit": "particle-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": workload_config(args, hs, world * n,
+            "config": workload_config(args, hs, world * n, world=world,
                                       note=None if world == 1 else
-                                      f"one periodic box cut into {world} z-slabs (one per GPU); halo layers and "
-                                      "migrating particles move with NCCL send/recv, message sizes with two small "
-                                      "all-gathers per step, the adaptive timestep with a one-word MAX all-reduce"),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d * world,
+                                      f"one periodic box cut into {world} z-slabs (one per GPU); transport "
+                                      f"{res['transport']}"),
+            "clocks": res["clocks"],
+            "e2e": {"value": res.get("e2e_value"), "unit": "particle-updates/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps,
-                    "what": "upload(host pos/vel/acc/types) + one core_step + download(host pos/vel/acc) through "
-                            "the C ABI, synchronised every step"},
-            "gpu_launches": launches,
+                    "what": "upload(pinned host pos/vel/acc/types) + one core_step + download(pinned host "
+                            "pos/vel/acc) through the C ABI, synchronised every step"},
+            "gpu_launches": res["launches"],
             "roofline": roofline,
         }
+        if "steady" in res:
+            line["steady_state"] = res["steady"]
+        if parity is not None:
+            line["parity_check"] = parity
+        if north is not None:
+            line["north_star_16m"] = north
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, args.seed, args.density, args.cpu_seconds)
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -76,6 +76,13 @@ SIGNATURES = {
     "gof_engine_set_graph": (_i, [_vp, _i]),
     "gof_engine_timing": (_i, [_vp, _i]),
     "gof_engine_force_time": (_i, [_vp, C.POINTER(_f), C.POINTER(_i)]),
+    "gof_slab_window": (_i, [_vp, _vp, _i]),
+    "gof_slab_connect": (_i, [_vp, _i, _i, _vp, _vp]),
+    "gof_slab_step_p2p": (_i, [_vp, _i, _i, C.c_float, _i, _vp, _vp]),
+    "gof_slab_check": (_i, [_vp, _vp, _vp]),
+    "gof_ipc_export": (_i, [_vp, _vp, _vp]),
+    "gof_ipc_open": (_i, [_vp, _vp]),
+    "gof_ipc_close": (_i, [_vp]),
     "gof_engine_pair_stats": (_i, [_vp, _i, _vp, _vp]),
     "gof_engine_last_timestep": (_i, [_vp, C.POINTER(_f), _vp]),
     "gof_slab_create": (_i, [C.POINTER(_vp), _i, _i, _i, C.POINTER(Grid), _vp, _i, _i, _i, _i]),
@@ -89,7 +96,7 @@ SIGNATURES = {
     "gof_slab_phase_force_boundary": (_i, [_vp, _i, _i, _i, _vp]),
     "gof_slab_parity": (_i, [_vp]),
     "gof_slab_count": (_i, [_vp]),
-    "gof_slab_download": (_i, [_vp] + [_vp] * 10 + [_vp]),
+    "gof_slab_download": (_i, [_vp] + [_vp] * 11 + [_vp]),
 }
 
 _lib = None

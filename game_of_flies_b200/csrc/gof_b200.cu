@@ -16,6 +16,7 @@
 
 #include "../../include/gof_b200.h"
 #include "gof_force.cuh"
+#include "gof_slab_p2p.cuh"
 
 using namespace gof;
 
@@ -570,6 +571,7 @@ __global__ void k_prepare_dt(StepScalars* s, int parity, float fixed_dt)
 }
 
 __global__ void k_bits_to_float(const unsigned* bits, float* out) { *out = __uint_as_float(*bits); }
+__global__ void k_set_word(int* p, int v) { *p = v; }
 
 }  // namespace gof
 
@@ -789,6 +791,23 @@ struct gof_engine {
     int n_slots = 0;        // resident slots before the sort (live + dead + arrivals)
     int lo_pop = 0, hi_pop = 0;  // populations of the two owned boundary layers (gof_slab_commit)
 
+    // peer-memory transport (gof_slab_connect / gof_slab_step_p2p): nothing about a step's sizes
+    // reaches the host; the neighbours' arenas are mapped into this process
+    char* arena_base = nullptr;
+    struct P2P {
+        bool on = false;
+        int rank = 0, world = 0;
+        PeerSide below{}, above{};
+        unsigned step = 0;          // tag of the last enqueued step
+        bool need_publish = true;   // the maximum speed of the resident state has not been published yet
+    } p2p;
+    unsigned long long* p2p_flags = nullptr;    // [0] records from below, [1] from above, [2] halo from below, [3] from above
+    unsigned long long* speed_in = nullptr;     // [2][kMaxWorld]: every slab's published maximum, per step parity
+    unsigned long long** speed_ptrs = nullptr;  // [2][kMaxWorld]: where this slab publishes to (device array)
+    int* push_done = nullptr;                   // [2] block counters of k_push_halo
+    int* halo_n = nullptr;                      // [2] sizes of the received halo layers
+    int* halo_count_in = nullptr;               // [2][cells per layer]: the neighbours' per-cell counts of their layers
+
     // One core_step captured as a CUDA graph per parity (8 kernels + a memset become one launch;
     // small systems are launch-bound).  Re-captured when anything baked into the nodes changes.
     struct StepGraph {
@@ -850,6 +869,14 @@ static size_t engine_layout(gof_engine* e, char* base)
             e->mig_recv[d] = (float4*)take(((size_t)e->mig_capacity * 3 + 1) * sizeof(float4));
         }
         e->counters = (int*)take(8 * sizeof(int));
+        // one block that peers write into / that holds peer pointers (offsets are part of gof_slab_window)
+        char* blk = take(1024);
+        e->p2p_flags = (unsigned long long*)blk;
+        e->speed_in = (unsigned long long*)(blk + 64);
+        e->speed_ptrs = (unsigned long long**)(blk + 64 + 2 * kMaxWorld * 8);
+        e->push_done = (int*)(blk + 64 + 4 * kMaxWorld * 8);
+        e->halo_n = e->push_done + 2;
+        e->halo_count_in = (int*)take(2 * (size_t)e->geom.nbx * e->geom.nby * sizeof(int));
     }
     return o;
 }
@@ -927,6 +954,8 @@ extern "C" int gof_engine_bind_arena(gof_engine* e, void* d_arena, size_t bytes)
     if ((uintptr_t)d_arena % 256) return fail(GOF_E_INVALID, "gof_engine_bind_arena: arena must be 256-byte aligned");
     GOF_CUDA(cudaSetDevice(e->device));
     engine_layout(e, (char*)d_arena);
+    e->arena_base = (char*)d_arena;
+    e->p2p = gof_engine::P2P{};
     e->bound = true;
     e->uploaded = e->binned = false;
     e->species_dirty = true;
@@ -1315,7 +1344,8 @@ __global__ void __launch_bounds__(kEwThreads)
 k_unpack_rest(const float4* __restrict__ posw, const float4* __restrict__ veli, const float4* __restrict__ acc,
               int n, float* __restrict__ px, float* __restrict__ py, float* __restrict__ pz,
               float* __restrict__ vx, float* __restrict__ vy, float* __restrict__ vz,
-              float* __restrict__ ax, float* __restrict__ ay, float* __restrict__ az, int* __restrict__ ids)
+              float* __restrict__ ax, float* __restrict__ ay, float* __restrict__ az, int* __restrict__ ids,
+              int* __restrict__ types)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -1324,6 +1354,7 @@ k_unpack_rest(const float4* __restrict__ posw, const float4* __restrict__ veli, 
     vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
     ax[k] = a.x; ay[k] = a.y; az[k] = a.z;
     ids[k] = __float_as_int(v.w);
+    types[k] = __float_as_int(p.w);
 }
 }  // namespace gof
 
@@ -1363,6 +1394,10 @@ extern "C" int gof_slab_upload(gof_engine* e, int n, const float* px, const floa
                    ax ? e->stage[6] : nullptr, ay ? e->stage[7] : nullptr, az ? e->stage[8] : nullptr,
                    e->stage_types, e->stage_bins, n, e->posw[0], e->veli[0], e->acc,
                    &e->scalars->max_sq_speed_bits[0]);
+    // the live count and the sticky error flag as the device-driven step reads them
+    GOF_CUDA(cudaMemsetAsync(e->counters, 0, 8 * sizeof(int), st));
+    GOF_LAUNCH(k_set_word, 1, 1, 0, st, e->counters + 4, n);
+    e->p2p.need_publish = true;
     e->uploaded = true;
     e->binned = false;
     return 0;
@@ -1565,6 +1600,295 @@ extern "C" int gof_slab_phase_force(gof_engine* e, int n_halo_lo, int n_halo_hi,
     return slab_force_boundary(e, n_halo_lo, n_halo_hi, wrap_mode, true, (cudaStream_t)stream);
 }
 
+// --------------------------------------------------------------------------------------
+// slab decomposition over peer memory: the neighbours' arenas are mapped into this process
+// (CUDA IPC between processes, plain pointers inside one), every exchange is a kernel that
+// stores into the neighbour and raises a tagged flag there, every wait is a one-block kernel
+// on the consumer's stream.  No size returns to the host during a run.
+// --------------------------------------------------------------------------------------
+static const char* p2p_error_text(int code)
+{
+    switch (code) {
+        case 1: return "slab: a particle moved more than one layer in a step, or arrived in the wrong slab";
+        case 2: return "slab: migration buffer overflow (raise migrate_capacity)";
+        case kErrPeerTimeout: return "slab: a neighbour's data did not arrive within 4 s (peer stalled or failed)";
+        case kErrHaloOverflow: return "slab: a boundary layer is larger than the neighbour's halo_capacity";
+        case 5: return "slab: particle capacity exceeded by arrivals";
+        default: return "slab: device-side error";
+    }
+}
+
+/* Synchronise `st`, fetch {live, bottom, top, -} and the sticky error flag, raise if it is set. */
+static int slab_p2p_sync_count(gof_engine* e, cudaStream_t st)
+{
+    int w[8];
+    GOF_CUDA(cudaMemcpyAsync(w, e->counters, sizeof(w), cudaMemcpyDeviceToHost, st));
+    GOF_CUDA(cudaStreamSynchronize(st));
+    if (w[2] != 0) return fail(w[2] == 2 || w[2] == 5 || w[2] == kErrHaloOverflow ? GOF_E_NOMEM : GOF_E_STATE, p2p_error_text(w[2]));
+    if (w[4] < 0 || w[4] > e->capacity) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
+    e->n = w[4];
+    e->lo_pop = w[5];
+    e->hi_pop = w[6];
+    return 0;
+}
+
+extern "C" int gof_slab_check(gof_engine* e, int* n_live, void* stream)
+{
+    if (int rc = slab_ready(e, true)) return rc;
+    if (int rc = slab_p2p_sync_count(e, (cudaStream_t)stream)) return rc;
+    if (n_live) *n_live = e->n;
+    return 0;
+}
+
+extern "C" int gof_slab_window(gof_engine* e, int64_t* info, int n_info)
+{
+    if (int rc = slab_ready(e, false)) return rc;
+    if (!info || n_info < 12) return fail(GOF_E_INVALID, "gof_slab_window: need room for 12 words");
+    auto off = [&](const void* p) { return (int64_t)((const char*)p - e->arena_base); };
+    info[0] = off(e->mig_recv[0]);
+    info[1] = off(e->mig_recv[1]);
+    info[2] = off(e->posw[1]);
+    info[3] = off(e->veli[1]);
+    info[4] = off(e->count);
+    info[5] = off(e->p2p_flags);
+    info[6] = e->capacity;
+    info[7] = e->halo_capacity;
+    info[8] = e->geom.nlz;
+    info[9] = e->mig_capacity;
+    info[10] = (int64_t)e->geom.nbx * e->geom.nby;
+    info[11] = off(e->halo_count_in);
+    return 0;
+}
+
+extern "C" int gof_slab_connect(gof_engine* e, int rank, int world, void* const* bases, const int64_t* infos)
+{
+    if (int rc = slab_ready(e, false)) return rc;
+    if (!bases || !infos || world < 2 || world > kMaxWorld || rank < 0 || rank >= world)
+        return fail(GOF_E_INVALID, "gof_slab_connect: bad arguments (2 <= world <= 16)");
+    const int64_t* mine = infos + 12 * rank;
+    if ((char*)bases[rank] != e->arena_base || mine[6] != e->capacity || mine[8] != e->geom.nlz)
+        return fail(GOF_E_INVALID, "gof_slab_connect: entry `rank` does not describe this slab");
+    if (e->layer_hi - e->layer_lo < 2)
+        return fail(GOF_E_INVALID, "gof_slab_connect: a slab needs at least two owned layers");
+    auto side = [&](int peer, bool peer_is_below, PeerSide* out) -> int {
+        const int64_t* pi = infos + 12 * peer;
+        char* b = (char*)bases[peer];
+        if (!b) return fail(GOF_E_INVALID, "gof_slab_connect: null peer base");
+        if (pi[9] != e->mig_capacity || pi[10] != (int64_t)e->geom.nbx * e->geom.nby)
+            return fail(GOF_E_INVALID, "gof_slab_connect: migrate_capacity and the layer shape must match on all slabs");
+        const int64_t cap = pi[6], hcap = pi[7], per_layer = pi[10];
+        unsigned long long* flags = (unsigned long long*)(b + pi[5]);
+        if (peer_is_below) {
+            // this slab is ABOVE the peer: records arrive there "from above", the bottom layer
+            // becomes the peer's UPPER halo (second halo region, count row of its last layer)
+            out->mig_recv = (float4*)(b + pi[1]);
+            out->halo_posw = (float4*)(b + pi[2]) + cap + hcap;
+            out->halo_veli = (float4*)(b + pi[3]) + cap + hcap;
+            out->halo_count = (int*)(b + pi[11]) + per_layer;
+            out->mig_flag = flags + 1;
+            out->halo_flag = flags + 3;
+        } else {
+            out->mig_recv = (float4*)(b + pi[0]);
+            out->halo_posw = (float4*)(b + pi[2]) + cap;
+            out->halo_veli = (float4*)(b + pi[3]) + cap;
+            out->halo_count = (int*)(b + pi[11]);
+            out->mig_flag = flags + 0;
+            out->halo_flag = flags + 2;
+        }
+        out->halo_capacity = (int)hcap;
+        return 0;
+    };
+    if (int rc = side((rank + world - 1) % world, true, &e->p2p.below)) return rc;
+    if (int rc = side((rank + 1) % world, false, &e->p2p.above)) return rc;
+    // where this slab publishes its maximum speed: slot `rank` of every slab's array, per parity
+    unsigned long long* ptrs[2 * kMaxWorld] = {};
+    for (int par = 0; par < 2; ++par)
+        for (int t = 0; t < world; ++t)
+            ptrs[par * kMaxWorld + t] = (unsigned long long*)((char*)bases[t] + infos[12 * t + 5] + 64) + par * kMaxWorld + rank;
+    GOF_CUDA(cudaMemcpy(e->speed_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
+    GOF_CUDA(cudaMemset(e->p2p_flags, 0, 64 + 2 * kMaxWorld * 8));
+    GOF_CUDA(cudaMemset(e->push_done, 0, 4 * sizeof(int)));
+    GOF_CUDA(cudaDeviceSynchronize());
+    e->p2p.on = true;
+    e->p2p.rank = rank;
+    e->p2p.world = world;
+    e->p2p.step = 0;
+    e->p2p.need_publish = true;
+    return 0;
+}
+
+/* n_steps x core_step over the local slabs of a job whose slabs are connected with
+ * gof_slab_connect.  Phases are enqueued slab by slab so that, when several slabs share a GPU
+ * (one process, tests), every store into a neighbour is enqueued before the wait for it.
+ * `side_stream` carries the halo traffic and the boundary layers under the interior forces. */
+extern "C" int gof_slab_step_p2p(gof_engine* const* slabs, int n_slabs, int n_steps, float timestep, int wrap_mode,
+                                 void* main_stream, void* side_stream)
+{
+    if (!slabs || n_slabs < 1) return fail(GOF_E_INVALID, "gof_slab_step_p2p: no slabs");
+    if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
+        return fail(GOF_E_INVALID, "gof_slab_step_p2p: bad wrap_mode");
+    if (timestep == 0.0f || timestep != timestep) return fail(GOF_E_INVALID, "gof_slab_step_p2p: bad timestep");
+    for (int s = 0; s < n_slabs; ++s) {
+        if (int rc = slab_ready(slabs[s], true)) return rc;
+        if (!slabs[s]->p2p.on) return fail(GOF_E_STATE, "gof_slab_step_p2p: call gof_slab_connect first");
+    }
+    cudaStream_t ms = (cudaStream_t)main_stream, ss = (cudaStream_t)side_stream;
+    if (!ss || ss == ms) return fail(GOF_E_INVALID, "gof_slab_step_p2p: needs a side stream");
+    const bool adaptive = timestep < 0;
+    static thread_local cudaEvent_t ev_sorted = nullptr, ev_done = nullptr;
+    if (!ev_sorted) {
+        GOF_CUDA(cudaEventCreateWithFlags(&ev_sorted, cudaEventDisableTiming));
+        GOF_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    }
+    for (int step = 0; step < n_steps; ++step) {
+        // ---- 1. bin, pack the leavers, push them to the neighbours ------------------------------
+        for (int s = 0; s < n_slabs; ++s) {
+            gof_engine* e = slabs[s];
+            const Geometry& g = e->geom;
+            const unsigned tag = ++e->p2p.step;
+            if (adaptive && e->p2p.need_publish)
+                GOF_LAUNCH(k_publish_speed, 1, 32, 0, ms, (const StepScalars*)e->scalars, e->parity,
+                           (unsigned long long* const*)(e->speed_ptrs + e->parity * kMaxWorld), e->p2p.world, tag);
+            e->p2p.need_publish = false;
+            GOF_CUDA(cudaMemsetAsync(e->count, 0, (size_t)(g.num_cells + 2) * sizeof(int), ms));
+            GOF_CUDA(cudaMemsetAsync(e->counters, 0, 2 * sizeof(int), ms));
+            GOF_CUDA(cudaMemsetAsync(e->mig_send[0], 0, sizeof(float4), ms));
+            GOF_CUDA(cudaMemsetAsync(e->mig_send[1], 0, sizeof(float4), ms));
+            MigrateOut mig{e->mig_send[0], e->mig_send[1], e->counters + 2, e->mig_capacity};
+            // (the live count of the resident state is a device word: launch over the capacity)
+            GOF_LAUNCH(k_hash_count<false>, cdiv(e->capacity, kBinThreads), kBinThreads, 0, ms, e->posw[0], e->veli[0],
+                       e->acc, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, e->capacity,
+                       (const int*)(e->counters + 4), g, e->cell_of, e->off, e->count, mig, (const int*)nullptr);
+            GOF_LAUNCH(k_push_migration, 2, kPushThreads, 0, ms, (const float4*)e->mig_send[0], (const float4*)e->mig_send[1],
+                       e->p2p.below, e->p2p.above, e->mig_capacity, tag);
+        }
+        // ---- 2. arrivals in, timestep, counting sort + kick ------------------------------------
+        for (int s = 0; s < n_slabs; ++s) {
+            gof_engine* e = slabs[s];
+            const Geometry& g = e->geom;
+            const unsigned tag = e->p2p.step;
+            int* words = e->counters;  // [0] arrivals, [1] slots in use, [2] sticky error, [4..7] sort results
+            GOF_LAUNCH(k_wait_tags, 1, 32, 0, ms, (const unsigned long long*)(e->p2p_flags + 0),
+                       (const unsigned long long*)(e->p2p_flags + 1), tag, (int*)nullptr, words + 2);
+            const int max_arrivals = 2 * e->mig_capacity;
+            GOF_LAUNCH(k_append_arrivals, cdiv(max_arrivals, kBinThreads), kBinThreads, 0, ms, (const float4*)e->mig_recv[0],
+                       (const float4*)e->mig_recv[1], e->mig_capacity, 0, e->posw[0], e->veli[0], e->acc, words,
+                       (const int*)(words + 4), e->capacity, words + 2);
+            MigrateOut flag_only{nullptr, nullptr, words + 2, 0};
+            GOF_LAUNCH(k_hash_count<false>, cdiv(max_arrivals, kBinThreads), kBinThreads, 0, ms, e->posw[0], e->veli[0],
+                       e->acc, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, e->capacity,
+                       (const int*)(words + 1), g, e->cell_of, e->off, e->count, flag_only, (const int*)(words + 4));
+            GOF_LAUNCH(k_prepare_dt_p2p, 1, 32, 0, ms, e->scalars, e->parity, adaptive ? -1.0f : timestep,
+                       (const unsigned long long*)(e->speed_in + e->parity * kMaxWorld), e->p2p.world, tag, words + 2);
+            if (int rc = launch_scan(e->count, g.num_cells + 1, e->tile_sums, e->start, ms)) return rc;
+            GOF_LAUNCH(k_scatter_ids<false>, cdiv(e->capacity, kBinThreads), kBinThreads, 0, ms, e->veli[0], e->capacity,
+                       (const int*)(words + 1), e->cell_of, e->off, e->start, e->slot_id, e->posw[0], engine_keys(e));
+            GOF_LAUNCH(k_rank_gather_kick, cdiv(e->capacity, kBinThreads), kBinThreads, 0, ms, e->capacity,
+                       (const int*)(words + 1), e->cell_of, e->start, e->count, e->slot_id, engine_keys(e), g.num_cells,
+                       e->posw[0], e->veli[0], e->acc, e->posw[1], e->veli[1], e->cell_sorted, e->scalars, 1);
+            GOF_LAUNCH(k_slab_counts, 1, 1, 0, ms, e->start, words + 2, words + 4, g.num_cells, g.nbx * g.nby, g.nlz - 2);
+            e->binned = true;
+        }
+        GOF_CUDA(cudaEventRecord(ev_sorted, ms));
+        GOF_CUDA(cudaStreamWaitEvent(ss, ev_sorted, 0));
+        // ---- 3a. interior forces (main stream) ------------------------------------------------
+        for (int s = 0; s < n_slabs; ++s) {
+            gof_engine* e = slabs[s];
+            if (e->layer_hi - e->layer_lo < 3) continue;  // no interior layer
+            ForceArgs a;
+            engine_force_args(e, wrap_mode, &a);
+            a.integrate = 1;
+            a.parity_out = e->parity ^ 1;
+            a.interior_words = e->counters + 4;
+            a.home_begin = 0;
+            a.home_count = e->capacity;  // upper bound of the owned particles
+            a.n_total = e->capacity;
+            if (int rc = slab_timed_force(e, a, ms)) return rc;
+        }
+        // ---- 3b. halo layers to the neighbours, then the boundary layers (side stream) ---------
+        for (int s = 0; s < n_slabs; ++s) {
+            gof_engine* e = slabs[s];
+            const Geometry& g = e->geom;
+            GOF_LAUNCH(k_push_halo, 2 * kHaloPushBlocks, kPushThreads, 0, ss, (const float4*)e->posw[1],
+                       (const float4*)e->veli[1], (const int*)e->count, (const int*)(e->counters + 4), g.nbx * g.nby,
+                       g.nlz - 2, e->species.has_boids ? 1 : 0, e->p2p.below, e->p2p.above, e->p2p.step, e->push_done);
+        }
+        for (int s = 0; s < n_slabs; ++s) {
+            gof_engine* e = slabs[s];
+            const Geometry& g = e->geom;
+            const int per_layer = g.nbx * g.nby;
+            GOF_LAUNCH(k_wait_tags, 1, 32, 0, ss, (const unsigned long long*)(e->p2p_flags + 2),
+                       (const unsigned long long*)(e->p2p_flags + 3), e->p2p.step, e->halo_n, e->counters + 2);
+            GOF_LAUNCH(k_halo_starts_p2p, 2, kScanThreads, 0, ss, (const int*)e->halo_count_in, e->count, e->start,
+                       per_layer, (g.nlz - 1) * per_layer, e->capacity, e->capacity + e->halo_capacity);
+            // the bottom and the top owned layer (with two owned layers: everything), ranges from
+            // the device words; the grid covers an upper bound of their population
+            ForceArgs a;
+            engine_force_args(e, wrap_mode, &a);
+            a.integrate = 1;
+            a.parity_out = e->parity ^ 1;
+            a.n_total = e->capacity;
+            a.boundary_words = e->counters + 4;
+            const int cap2 = 2 * e->halo_capacity;
+            a.home_count = cap2 < e->capacity ? cap2 : e->capacity;
+            if (int rc = slab_timed_force(e, a, ss)) return rc;
+        }
+        GOF_CUDA(cudaEventRecord(ev_done, ss));
+        GOF_CUDA(cudaStreamWaitEvent(ms, ev_done, 0));
+        // ---- 4. the new velocities' maximum goes to every slab (next step's timestep) -----------
+        for (int s = 0; s < n_slabs; ++s) {
+            gof_engine* e = slabs[s];
+            e->parity ^= 1;
+            if (adaptive)
+                GOF_LAUNCH(k_publish_speed, 1, 32, 0, ms, (const StepScalars*)e->scalars, e->parity,
+                           (unsigned long long* const*)(e->speed_ptrs + e->parity * kMaxWorld), e->p2p.world,
+                           e->p2p.step + 1);
+            else
+                e->p2p.need_publish = true;  // (a later adaptive step must publish first)
+        }
+    }
+    return 0;
+}
+
+/* CUDA IPC plumbing for gof_slab_connect between processes: export the allocation that holds
+ * `d_ptr` (64-byte handle + offset of d_ptr inside it), open a peer's handle, close it. */
+extern "C" int gof_ipc_export(const void* d_ptr, void* handle64, int64_t* offset)
+{
+    if (!d_ptr || !handle64 || !offset) return fail(GOF_E_INVALID, "gof_ipc_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    // base of the allocation: driver entry point through the runtime (no link-time libcuda)
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    GOF_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) return fail(GOF_E_STATE, "gof_ipc_export: cuMemGetAddressRange unavailable");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (int cr = ((range_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)d_ptr))
+        return fail(GOF_E_STATE, "gof_ipc_export: cuMemGetAddressRange failed (" + std::to_string(cr) + ")");
+    cudaIpcMemHandle_t h;
+    GOF_CUDA(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
+    std::memcpy(handle64, &h, 64);
+    *offset = (int64_t)((unsigned long long)(uintptr_t)d_ptr - base);
+    return 0;
+}
+
+extern "C" int gof_ipc_open(const void* handle64, void** d_base)
+{
+    if (!handle64 || !d_base) return fail(GOF_E_INVALID, "gof_ipc_open: null pointer");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    GOF_CUDA(cudaIpcOpenMemHandle(d_base, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int gof_ipc_close(void* d_base)
+{
+    if (!d_base) return 0;
+    GOF_CUDA(cudaIpcCloseMemHandle(d_base));
+    return 0;
+}
+
 /* Current parity (which of the two max-speed slots describes the resident velocities). */
 extern "C" int gof_slab_parity(const gof_engine* e) { return e ? e->parity : 0; }
 extern "C" int gof_slab_count(const gof_engine* e) { return e ? e->n : 0; }
@@ -1572,18 +1896,21 @@ extern "C" int gof_slab_count(const gof_engine* e) { return e ? e->n : 0; }
 /* State in rest order with the particle ids (the host scatters by id).  Arrays hold
  * gof_slab_count() entries; pointers may be host or device. */
 extern "C" int gof_slab_download(gof_engine* e, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
-                                 float* ax, float* ay, float* az, int32_t* ids, void* stream)
+                                 float* ax, float* ay, float* az, int32_t* ids, int32_t* types, void* stream)
 {
     if (int rc = slab_ready(e, true)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (e->p2p.on)
+        if (int rc = slab_p2p_sync_count(e, st)) return rc;
     const int n = e->n;
     if (n == 0) return 0;
     GOF_LAUNCH(k_unpack_rest, cdiv(n, kEwThreads), kEwThreads, 0, st, e->posw[0], e->veli[0], e->acc, n, e->stage[0],
                e->stage[1], e->stage[2], e->stage[3], e->stage[4], e->stage[5], e->stage[6], e->stage[7],
-               e->stage[8], e->stage_bins);
+               e->stage[8], e->stage_bins, e->stage_types);
     float* dst[9] = {px, py, pz, vx, vy, vz, ax, ay, az};
     for (int k = 0; k < 9; ++k)
         if (dst[k]) GOF_CUDA(cudaMemcpyAsync(dst[k], e->stage[k], (size_t)n * sizeof(float), cudaMemcpyDefault, st));
     if (ids) GOF_CUDA(cudaMemcpyAsync(ids, e->stage_bins, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
+    if (types) GOF_CUDA(cudaMemcpyAsync(types, e->stage_types, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
     return 0;
 }

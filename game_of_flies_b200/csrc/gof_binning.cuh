@@ -48,9 +48,10 @@ k_hash_count(const float4* __restrict__ posw, const float4* __restrict__ veli,
              const float* __restrict__ py, const float* __restrict__ pz, int n,
              const int* __restrict__ n_limit, const __grid_constant__ Geometry g,
              int* __restrict__ cell_of, int* __restrict__ off, int* __restrict__ count,
-             MigrateOut mig)
+             MigrateOut mig, const int* __restrict__ base_word = nullptr)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // base_word (slab mode, peer-memory transport): the first slot to look at lives on the device
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + (base_word ? *base_word : 0);
     if (n_limit) n = min(n, *n_limit);  // slab mode: the real count lives on the device
     int cell = -1;
     if (i < n) {
@@ -332,10 +333,20 @@ namespace gof {
 __global__ void __launch_bounds__(kBinThreads)
 k_append_arrivals(const float4* __restrict__ from_down, const float4* __restrict__ from_up, int capacity,
                   int base, float4* __restrict__ posw, float4* __restrict__ veli,
-                  float4* __restrict__ acc, int* __restrict__ words)
+                  float4* __restrict__ acc, int* __restrict__ words,
+                  const int* __restrict__ base_word = nullptr, int slot_capacity = 0, int* error = nullptr)
 {
-    const int n_down = min(__float_as_int(from_down[0].x), capacity);
-    const int n_up = min(__float_as_int(from_up[0].x), capacity);
+    int n_down = min(__float_as_int(from_down[0].x), capacity);
+    int n_up = min(__float_as_int(from_up[0].x), capacity);
+    if (base_word) {
+        // peer-memory transport: the number of resident slots lives on the device, and so does the
+        // check that the arrivals fit (the host learns of a failure from the sticky error flag)
+        base = *base_word;
+        if (base + n_down + n_up > slot_capacity) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(error, 5);
+            n_down = n_up = 0;
+        }
+    }
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) {
         words[0] = n_down + n_up;

@@ -193,7 +193,29 @@ __global__ void k_prepare_dt_p2p(StepScalars* s, int parity, float fixed_dt,
     }
 }
 
-// Halo cell table with the halo regions at FIXED slots (capacity, capacity + halo_capacity): see
-// k_halo_starts; nothing about the halo sizes is needed on the host.
+// Halo cell table with the halo regions at FIXED slots (capacity, capacity + halo_capacity), so
+// nothing about the halo sizes is needed on the host.  The neighbours deliver the per-cell counts
+// of their layers into `count_in` (two rows of cells_per_layer) -- not into the count table
+// itself, which this slab is still scanning when a fast neighbour's push arrives -- and this
+// kernel copies them into the rows of the two halo layers next to the cell starts.
+__global__ void __launch_bounds__(kScanThreads)
+k_halo_starts_p2p(const int* __restrict__ count_in, int* __restrict__ count, int* __restrict__ start,
+                  int cells_per_layer, int first_cell_hi, int base_lo, int base_hi)
+{
+    const int first = blockIdx.x ? first_cell_hi : 0;
+    const int* in = count_in + (blockIdx.x ? cells_per_layer : 0);
+    int carry = blockIdx.x ? base_hi : base_lo;
+    for (int b = 0; b < cells_per_layer; b += kScanThreads) {
+        const int idx = b + threadIdx.x;
+        const int v = idx < cells_per_layer ? in[idx] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, total);
+        if (idx < cells_per_layer) {
+            count[first + idx] = v;
+            start[first + idx] = carry + ex;
+        }
+        carry += total;
+    }
+}
 
 }  // namespace gof

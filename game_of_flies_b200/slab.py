@@ -13,13 +13,24 @@ particles whose bin layer lies in [layer_lo, layer_hi) and, per step,
   3. computes forces for the owned particles over the local grid (owned layers +
      one halo layer each side) and integrates.
 
-`SlabRunner` sequences these phases and moves the buffers: with NCCL send/recv
-over NVLink when every process drives one slab (`DistComm`), or with plain device
-copies when several slabs live in one process (`LocalComm`, used to test the CUDA
-path on a single GPU).  The only collectives are tiny: one all-gather of four
-words per slab and step (the halo message sizes) and, with the adaptive timestep,
-a MAX all-reduce of one word; the halo traffic runs under the interior forces.  The physics is that of the single-GPU engine, bit for bit: the same
-cells, the same order inside a cell (by particle id), the same summation order.
+Two transports move the buffers:
+
+* `P2PRunner` (default on one node): the slabs map each other's arenas (CUDA IPC
+  between processes) and the exchange steps are kernels that STORE into the
+  neighbour's memory over NVLink and raise tagged flags there; one-block kernels on
+  the consumer's stream wait for the flags.  A step is one C call that enqueues a
+  fixed sequence of launches: no host synchronisation, no library collective, no
+  size ever returns to the host (csrc/gof_slab_p2p.cuh).
+* `SlabRunner` sequences the same phases from Python and moves the buffers with
+  NCCL send/recv when every process drives one slab (`DistComm`; gloo in the CPU
+  tests), or with plain device copies when several slabs live in one process
+  (`LocalComm`).  Its only collectives are tiny: one all-gather of four words per
+  slab and step (the halo message sizes) and, with the adaptive timestep, a MAX
+  all-reduce of one word; the halo traffic runs under the interior forces.
+
+The physics is that of the single-GPU engine, bit for bit, on either transport: the
+same cells, the same order inside a cell (by x, ties by particle id), the same
+summation order.
 """
 from __future__ import annotations
 
@@ -112,27 +123,57 @@ class SlabEngine:
             pass
 
     # ---- state -------------------------------------------------------------------------------
-    def upload(self, pos, types, ids, vel=None, acc=None):
-        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-        p = [f(a) for a in pos]
-        v = [f(a) for a in vel] if vel is not None else [None] * 3
-        a_ = [f(a) for a in acc] if acc is not None else [None] * 3
-        t = np.ascontiguousarray(types, dtype=np.int32)
-        i = np.ascontiguousarray(ids, dtype=np.int32)
-        ptr = lambda x: x.ctypes.data if x is not None else 0
-        _lib.check(self.lib.gof_slab_upload(self._handle, int(t.size), *[ptr(x) for x in p], *[ptr(x) for x in v],
-                                            *[ptr(x) for x in a_], ptr(t), ptr(i), self._stream()))
+    def upload(self, pos, types, ids, vel=None, acc=None, n=None):
+        """pos / vel / acc: three fp32 arrays each; numpy arrays, or (pinned) CPU / CUDA tensors of
+        which the first `n` entries are used (no staging copy on the host)."""
+        from .engine import _any_ptr
+
+        def f(a, dt):
+            if a is None or isinstance(a, torch.Tensor):
+                return a
+            return np.ascontiguousarray(a, dtype=dt)
+        p = [f(a, np.float32) for a in pos]
+        v = [f(a, np.float32) for a in vel] if vel is not None else [None] * 3
+        a_ = [f(a, np.float32) for a in acc] if acc is not None else [None] * 3
+        t, i = f(types, np.int32), f(ids, np.int32)
+        count = int(n) if n is not None else int(t.numel() if isinstance(t, torch.Tensor) else t.size)
+        _lib.check(self.lib.gof_slab_upload(self._handle, count, *[_any_ptr(x) for x in p], *[_any_ptr(x) for x in v],
+                                            *[_any_ptr(x) for x in a_], _any_ptr(t), _any_ptr(i), self._stream()))
         torch.cuda.current_stream(self.index).synchronize()
 
+    def count(self) -> int:
+        """Live particles of this slab (synchronises; raises a pending device-side error)."""
+        n = C.c_int()
+        _lib.check(self.lib.gof_slab_check(self._handle, C.byref(n), self._stream()))
+        return int(n.value)
+
     def download(self):
-        n = int(self.lib.gof_slab_count(self._handle))
+        n = self.count()
         out = {k: np.empty((3, n), dtype=np.float32) for k in ("pos", "vel", "acc")}
         ids = np.empty(n, dtype=np.int32)
+        types = np.empty(n, dtype=np.int32)
         ptrs = [out[k][c].ctypes.data for k in ("pos", "vel", "acc") for c in range(3)]
-        _lib.check(self.lib.gof_slab_download(self._handle, *ptrs, ids.ctypes.data, self._stream()))
+        _lib.check(self.lib.gof_slab_download(self._handle, *ptrs, ids.ctypes.data, types.ctypes.data, self._stream()))
         torch.cuda.current_stream(self.index).synchronize()
         out["ids"] = ids
+        out["types"] = types
         return out
+
+    def download_into(self, pos, vel, acc, ids, types) -> int:
+        """The state in rest order into caller-owned buffers of at least `capacity` entries (pinned
+        tensors: no allocation, no staging); returns the particle count (synchronises)."""
+        from .engine import _any_ptr
+        n = self.count()
+        ptrs = [_any_ptr(x) for grp in (pos, vel, acc) for x in grp]
+        _lib.check(self.lib.gof_slab_download(self._handle, *ptrs, _any_ptr(ids), _any_ptr(types), self._stream()))
+        torch.cuda.current_stream(self.index).synchronize()
+        return n
+
+    def pair_stats(self) -> dict:
+        out = (C.c_ulonglong * 3)()
+        _lib.check(self.lib.gof_engine_pair_stats(self._handle, self.wrap_mode, out, self._stream()))
+        return {"n": max(self.count(), 1), "candidates": int(out[0]),
+                "evaluated": int(out[1]), "in_range": int(out[2])}
 
     def set_parameters(self, parameter_matrix):
         pm = np.ascontiguousarray(parameter_matrix, dtype=np.float64)
@@ -458,6 +499,9 @@ class SlabRunner:
                 self.phase_ms["forces"] += marks[1].elapsed_time(marks[2])
                 self.phase_ms["steps"] += 1
 
+    def close(self):
+        pass
+
     def gather_state(self, num_particles: int):
         """This process's particles scattered into (3, N) arrays by id (others stay NaN)."""
         out = {k: np.full((3, num_particles), np.nan, dtype=np.float32) for k in ("pos", "vel", "acc")}
@@ -469,6 +513,113 @@ class SlabRunner:
             owner[d["ids"]] = s
         out["owner"] = owner
         return out
+
+
+class P2PRunner:
+    """The slabs of a job exchange through peer memory (gof_slab_connect / gof_slab_step_p2p).
+
+    `slabs`: {global slab index: SlabEngine} of this process.  With torch.distributed initialised
+    (one slab per rank is the normal case) the arenas are shared with CUDA IPC: every rank exports
+    a handle, all-gathers handles and window descriptions once, and maps its peers.  Without it all
+    slabs must be local (tests on one GPU).  A step is ONE C call; nothing is read back."""
+
+    transport = "p2p (peer-memory stores over NVLink, flag waits on the stream, no host sync)"
+
+    def __init__(self, slabs: dict, world_slabs: int, group_ready: bool | None = None):
+        self.slabs = dict(slabs)
+        self.world_slabs = int(world_slabs)
+        self.lib = _lib.load()
+        self.phase_ms = None
+        self._opened = []
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized() if group_ready is None else group_ready
+        first = next(iter(self.slabs.values()))
+        self.index = first.index
+        if any(e.index != self.index for e in self.slabs.values()):
+            raise ValueError("P2PRunner: the local slabs must share one device")
+        W = self.world_slabs
+        infos = {}
+        for s, e in self.slabs.items():
+            w = (C.c_int64 * 12)()
+            _lib.check(self.lib.gof_slab_window(e._handle, w, 12))
+            infos[s] = list(w)
+        bases = {s: e._arena_ptr for s, e in self.slabs.items()}
+        if len(self.slabs) < W:
+            if not distributed:
+                raise ValueError("P2PRunner: slabs missing and torch.distributed is not initialised")
+            mine = {}
+            for s, e in self.slabs.items():
+                h = (C.c_ubyte * 64)()
+                off = C.c_int64()
+                _lib.check(self.lib.gof_ipc_export(e._arena_ptr, h, C.byref(off)))
+                mine[s] = (bytes(h), int(off.value), infos[s], torch.cuda.current_device())
+            gathered = [None] * dist.get_world_size()
+            dist.all_gather_object(gathered, mine)
+            for part in gathered:
+                for s, (h, off, info, _dev) in part.items():
+                    infos[s] = info
+                    if s in self.slabs:
+                        continue
+                    base = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                    with torch.cuda.device(self.index):
+                        _lib.check(self.lib.gof_ipc_open(buf, C.byref(base)))
+                    self._opened.append(base.value)
+                    bases[s] = base.value + off
+        if sorted(bases) != list(range(W)):
+            raise ValueError(f"P2PRunner: need every slab 0..{W - 1}, have {sorted(bases)}")
+        base_arr = (C.c_void_p * W)(*[bases[s] for s in range(W)])
+        info_arr = (C.c_int64 * (12 * W))(*[x for s in range(W) for x in infos[s]])
+        with torch.cuda.device(self.index):
+            for s, e in self.slabs.items():
+                _lib.check(self.lib.gof_slab_connect(e._handle, s, W, base_arr, info_arr))
+            torch.cuda.synchronize(self.index)
+        if distributed:
+            dist.barrier()  # every slab's flag block is zeroed before anybody stores into it
+        self._handles = (C.c_void_p * len(self.slabs))(*[self.slabs[s]._handle for s in sorted(self.slabs)])
+        self._side = torch.cuda.Stream(device=self.index, priority=-1)
+        self._distributed = distributed
+
+    def step(self, n_steps: int = 1, timestep=None):
+        first = next(iter(self.slabs.values()))
+        ts = -1.0 if timestep is None else float(timestep)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.gof_slab_step_p2p(self._handles, len(self.slabs), int(n_steps), ts, first.wrap_mode,
+                                                  torch.cuda.current_stream(self.index).cuda_stream,
+                                                  self._side.cuda_stream))
+
+    def gather_state(self, num_particles: int):
+        return SlabRunner.gather_state(self, num_particles)
+
+    def close(self):
+        """Unmap the peers (every rank must have finished stepping: barrier first)."""
+        if self._opened:
+            torch.cuda.synchronize(self.index)
+            if self._distributed:
+                import torch.distributed as dist
+                dist.barrier()
+            for b in self._opened:
+                self.lib.gof_ipc_close(b)
+            self._opened = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_runner(eng, world: int, device=None, transport: str = "auto"):
+    """The runner of a one-slab-per-rank job (torch.distributed initialised): peer-memory
+    transport unless `transport == "nccl"` (or GOF_SLAB_TRANSPORT=nccl)."""
+    import torch.distributed as dist
+    choice = os.environ.get("GOF_SLAB_TRANSPORT", transport)
+    rank = dist.get_rank()
+    if choice in ("auto", "p2p"):
+        return P2PRunner({rank: eng}, world)
+    runner = SlabRunner({rank: eng}, world, DistComm(world, device=device))
+    runner.transport = "nccl (send/recv of halo layers and migration records, sizes all-gathered per step)"
+    return runner
 
 
 def assign_to_slabs(pos_z, grid_bin_size_z: float, num_layers: int, layers):

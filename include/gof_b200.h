@@ -266,7 +266,44 @@ int gof_slab_parity(const gof_engine *e);
 int gof_slab_count(const gof_engine *e);
 int gof_slab_download(gof_engine *e, float *pos_x_any, float *pos_y_any, float *pos_z_any,
                       float *vel_x_any, float *vel_y_any, float *vel_z_any, float *acc_x_any,
-                      float *acc_y_any, float *acc_z_any, int32_t *ids_any, void *stream);
+                      float *acc_y_any, float *acc_z_any, int32_t *ids_any, int32_t *types_any,
+                      void *stream);
+
+
+/* ------------------------------------------------------------------------
+ * Slab decomposition over PEER MEMORY (the default transport on one node).  The slabs of a
+ * job map each other's arenas (CUDA IPC between processes; plain pointers inside one) and a
+ * step is enqueued without any host synchronisation or library collective:
+ *   leavers and boundary layers are STORED into the neighbours' memory by kernels, tagged flag
+ *   words announce them, one-block kernels on the consumer's stream wait for the flags, the
+ *   maximum speed of the adaptive timestep goes to every slab the same way, and the sizes of a
+ *   step (live particles, boundary layers, halo layers) never leave the device.
+ * Results are bit-identical to the single-GPU engine and to the send/recv transport above.
+ *
+ *   gof_slab_window   12 words describing what peers write into: byte offsets inside the arena
+ *                     of {records from below, records from above, cell-ordered positions,
+ *                     velocities, cell counts, flag block}, then capacity, halo_capacity, local
+ *                     layers, migrate_capacity, cells per layer, offset of the halo count rows
+ *   gof_slab_connect  bases[t] = slab t's arena base as mapped in THIS process (this slab's own
+ *                     base at index `rank`), infos = the `world` windows back to back.  All slabs
+ *                     must have connected (and synchronised their devices) before any of them steps.
+ *   gof_slab_step_p2p n_steps x core_step over this process's slabs (normally one); `side_stream`
+ *                     carries the halo traffic and the boundary layers under the interior forces.
+ *   gof_slab_check    synchronise `stream`, raise the slab's sticky device-side error if any
+ *                     (capacity, buffer overflow, a neighbour that stopped answering for 4 s) and
+ *                     return the live particle count.
+ * ---------------------------------------------------------------------- */
+int gof_slab_window(gof_engine *e, int64_t *info, int n_info);
+int gof_slab_connect(gof_engine *e, int rank, int world, void *const *bases, const int64_t *infos);
+int gof_slab_step_p2p(gof_engine *const *slabs, int n_slabs, int n_steps, float timestep, int wrap_mode,
+                      void *main_stream, void *side_stream);
+int gof_slab_check(gof_engine *e, int *n_live, void *stream);
+
+/* CUDA IPC plumbing for gof_slab_connect between processes: the 64-byte handle of the device
+ * allocation that holds d_ptr and d_ptr's offset inside it; open / close a peer's handle. */
+int gof_ipc_export(const void *d_ptr, void *handle64, int64_t *offset);
+int gof_ipc_open(const void *handle64, void **d_base);
+int gof_ipc_close(void *d_base);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,4 @@
-"""Multi-GPU check of the slab path over NCCL (needs >= 2 GPUs; launch with torchrun):
+"""Multi-GPU check of the slab path, both transports (needs >= 2 GPUs; launch with torchrun):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
         --master-port 29511 tests/run_slab_nccl.py
@@ -27,14 +27,16 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     from game_of_flies_b200.engine import ParticleEngine
-    from game_of_flies_b200.slab import (DistComm, SlabEngine, SlabRunner, assign_to_slabs, nccl_options,
-                                         split_layers)
+    from game_of_flies_b200.slab import SlabEngine, assign_to_slabs, make_runner, nccl_options, split_layers
     dist.init_process_group("nccl", device_id=device, pg_options=nccl_options())
 
     ok = True
-    for kinds, counts, limits, speed, timestep in [
-        ("clusters", [20000] * 5, (160, 160, 60 * world), 4.0, None),
-        ("mixed", [6000] * 6, (110, 110, 55 * world), 8.0, 0.03),
+    for transport, kinds, counts, limits, speed, timestep in [
+        ("p2p", "clusters", [20000] * 5, (160, 160, 60 * world), 4.0, None),
+        ("p2p", "mixed", [6000] * 6, (110, 110, 55 * world), 8.0, 0.03),
+        ("p2p", "boids", [20000] * 3, (120, 120, 50 * world), 9.0, None),
+        ("nccl", "clusters", [20000] * 5, (160, 160, 60 * world), 4.0, None),
+        ("nccl", "mixed", [6000] * 6, (110, 110, 55 * world), 8.0, 0.03),
     ]:
         st = random_state(counts, limits, seed=31, kinds=kinds, speed=speed)
         grid = orc.grid_from_limits(st["limits"], st["r_max"])
@@ -44,9 +46,10 @@ def main():
         e = SlabEngine(st["parameter_matrix"], st["limits"], st["r_max"], layers[rank][0], layers[rank][1],
                        capacity=int(m.sum() * 1.5) + 4096, device=device)
         e.upload(st["pos"][:, m], st["types"][m], np.nonzero(m)[0], vel=st["vel"][:, m], acc=st["acc"][:, m])
-        runner = SlabRunner({rank: e}, world, DistComm(world, device=device))
+        runner = make_runner(e, world, device, transport=transport)
         steps = 10
-        runner.step(steps, timestep)
+        runner.step(steps // 2, timestep)
+        runner.step(steps - steps // 2, timestep)
         got = runner.gather_state(st["n"])
         mine = got["owner"] >= 0
         cnt = torch.tensor([int(mine.sum())], device=device)
@@ -61,9 +64,10 @@ def main():
         good = torch.tensor([1 if same else 0], device=device)
         dist.all_reduce(good, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print(f"{kinds}: world={world} particles={st['n']} owned_total={int(cnt.item())} "
+            print(f"{transport} {kinds}: world={world} particles={st['n']} owned_total={int(cnt.item())} "
                   f"bit_identical={bool(good.item())}", flush=True)
         ok = ok and bool(good.item()) and int(cnt.item()) == st["n"]
+        runner.close()
         e.close(); single.close()
     dist.barrier()
     dist.destroy_process_group()

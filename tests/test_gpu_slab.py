@@ -1,7 +1,8 @@
 """The CUDA slab path on ONE GPU: several SlabEngine instances in one process exchange
-migration records and halo layers through LocalComm (device copies instead of NCCL), and
-must reproduce the single-engine result bit for bit: same cells, same order inside a cell,
-same summation order."""
+migration records and halo layers -- through the peer-memory transport (P2PRunner: the same
+kernels that store into a neighbour on another GPU, here into another arena of this GPU) and
+through LocalComm (device copies in place of NCCL send/recv) -- and must reproduce the
+single-engine result bit for bit: same cells, same order inside a cell, same summation order."""
 import numpy as np
 import pytest
 
@@ -23,8 +24,9 @@ def run_single(st, steps, timestep, wrap_mode):
     return out
 
 
-def run_slabs(st, world_slabs, steps, timestep, wrap_mode, overlap=True):
-    from game_of_flies_b200.slab import LocalComm, SlabEngine, SlabRunner, assign_to_slabs, split_layers
+def run_slabs(st, world_slabs, steps, timestep, wrap_mode, overlap=True, transport="copies"):
+    from game_of_flies_b200.slab import (LocalComm, P2PRunner, SlabEngine, SlabRunner, assign_to_slabs,
+                                         split_layers)
     grid = orc.grid_from_limits(st["limits"], st["r_max"])
     layers = split_layers(grid["num_bin_z"], world_slabs)
     owner = assign_to_slabs(st["pos"][2], grid["bin_size_z"], grid["num_bin_z"], layers)
@@ -35,10 +37,16 @@ def run_slabs(st, world_slabs, steps, timestep, wrap_mode, overlap=True):
                        wrap_mode=wrap_mode)
         e.upload(st["pos"][:, m], st["types"][m], np.nonzero(m)[0], vel=st["vel"][:, m], acc=st["acc"][:, m])
         slabs[s] = e
-    runner = SlabRunner(slabs, world_slabs, LocalComm(world_slabs), overlap=overlap)
-    runner.step(steps, timestep)
+    if transport == "p2p":
+        runner = P2PRunner(slabs, world_slabs, group_ready=False)
+    else:
+        runner = SlabRunner(slabs, world_slabs, LocalComm(world_slabs), overlap=overlap)
+    # in two calls: the second continues from device-resident counts
+    runner.step(steps // 2, timestep)
+    runner.step(steps - steps // 2, timestep)
     out = runner.gather_state(st["n"])
     moved = int((out["owner"] != owner).sum())
+    runner.close()
     for e in slabs.values():
         e.close()
     return out, moved
@@ -62,3 +70,34 @@ def test_slabs_reproduce_single_engine_bit_for_bit(kinds, counts, limits, speed,
         assert moved > 0, "the run should exercise migration between slabs"
         for k in ("pos", "vel", "acc"):
             assert np.array_equal(got[k], want[k]), f"{k} differs from the single-engine result"
+        # the peer-memory transport: stores into the neighbour's arena, flag waits, device-side sizes
+        got, moved = run_slabs(st, world_slabs, steps, timestep, wrap_mode, transport="p2p")
+        assert (got["owner"] >= 0).all() and moved > 0
+        for k in ("pos", "vel", "acc"):
+            assert np.array_equal(got[k], want[k]), f"p2p transport: {k} differs from the single-engine result"
+
+
+def test_p2p_slab_errors_surface_on_the_host():
+    """Device-side failures of the peer-memory transport raise at the next host read: a migration
+    buffer that overflows (tiny migrate_capacity, fast particles) must not pass silently."""
+    from game_of_flies_b200 import _lib
+    from game_of_flies_b200.slab import P2PRunner, SlabEngine, assign_to_slabs, split_layers
+    st = random_state([6000] * 3, (100, 100, 200), seed=5, kinds="clusters", speed=15.0)
+    grid = orc.grid_from_limits(st["limits"], st["r_max"])
+    layers = split_layers(grid["num_bin_z"], 2)
+    owner = assign_to_slabs(st["pos"][2], grid["bin_size_z"], grid["num_bin_z"], layers)
+    slabs = {}
+    for s, (lo, hi) in enumerate(layers):
+        m = owner == s
+        e = SlabEngine(st["parameter_matrix"], st["limits"], st["r_max"], lo, hi, capacity=int(m.sum() * 1.5) + 4096,
+                       migrate_capacity=2)
+        e.upload(st["pos"][:, m], st["types"][m], np.nonzero(m)[0], vel=st["vel"][:, m], acc=st["acc"][:, m])
+        slabs[s] = e
+    runner = P2PRunner(slabs, 2, group_ready=False)
+    runner.step(30, 0.05)
+    with pytest.raises(_lib.GofError, match="migration buffer overflow"):
+        for e in slabs.values():
+            e.count()
+    runner.close()
+    for e in slabs.values():
+        e.close()
