@@ -49,6 +49,47 @@ static int fail(int code, const std::string& msg)
     } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Every entry point runs on its engine's (or its buffers') device and leaves the caller's
+// current device as it found it.
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    explicit DeviceGuard(int device) : want(device)
+    {
+        if (device < 0 || cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// device that owns a device pointer (-1: not a device pointer / unknown: stay on the current device)
+static int device_of(const void* p)
+{
+    cudaPointerAttributes at{};
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : -1;
+}
+
+// SM count of the current device (queried once per device)
+static int sm_count()
+{
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev].store(v, std::memory_order_relaxed);
+    return v;
+}
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 
@@ -326,7 +367,6 @@ static int launch_force_t(const Geometry& g, const ForceArgs& a, cudaStream_t st
 // systems are latency-bound with one thread per particle: split the 9 (3 in 2D) stencil rows over
 // warps while the launch still fits the GPU a few times over.  Results do not depend on it.
 static int g_force_split = -1;  // -1: automatic
-static constexpr int kResidentWarps = 148 * 20;
 
 static int pick_split(const Geometry& g, int homes, bool boids)
 {
@@ -336,6 +376,7 @@ static int pick_split(const Geometry& g, int homes, bool boids)
     // at the reference density): 3D -- 9 warps up to ~150k particles, 3 warps up to ~350k;
     // 2D -- 3 warps up to ~50k
     const long warps = cdiv(homes, 32);
+    const long kResidentWarps = 20L * sm_count();  // (thresholds measured on 148 SMs)
     if (g.is3d) {
         if (warps * 9 <= 14L * kResidentWarps) return 9;
         if (warps * 3 <= 11L * kResidentWarps) return 3;
@@ -370,9 +411,11 @@ static int launch_force_m(const Geometry& g, const ForceArgs& a, int kind, cudaS
 }
 
 // a.home_count is the number of threads to launch (an upper bound when a.interior_words is set)
-static int launch_force(const Geometry& g, const ForceArgs& a, int kind, int mode, cudaStream_t st)
+static int launch_force(const Geometry& g, const ForceArgs& a0, int kind, int mode, cudaStream_t st)
 {
-    if (a.home_count + a.home_count2 <= 0) return 0;
+    if (a0.home_count + a0.home_count2 <= 0) return 0;
+    ForceArgs a = a0;
+    a.wave_sms = sm_count();
     if (mode == kModeIntegrate) return launch_force_m<kModeIntegrate>(g, a, kind, st);
     return launch_force_m<kModeScatter>(g, a, kind, st);
 }
@@ -596,6 +639,7 @@ extern "C" int gof_setup_bins(const float* d_pos_x, const float* d_pos_y, const 
                               int32_t* d_particle_indices, void* d_workspace, size_t workspace_bytes,
                               void* stream)
 {
+    DeviceGuard guard(device_of(d_pos_x));  // the arrays' device, whatever the caller's current one
     cudaStream_t st = (cudaStream_t)stream;
     Geometry g;
     if (int rc = make_geometry(grid, 0, 0, &g)) return rc;
@@ -638,6 +682,7 @@ extern "C" int gof_accelerator(const float* d_pos_x, const float* d_pos_y, const
                                const int32_t* d_bin_counts, int wrap_mode, void* d_workspace,
                                size_t workspace_bytes, void* stream)
 {
+    DeviceGuard guard(device_of(d_pos_x));  // the arrays' device, whatever the caller's current one
     cudaStream_t st = (cudaStream_t)stream;
     Geometry g;
     if (int rc = make_geometry(grid, 0, 0, &g)) return rc;
@@ -708,6 +753,7 @@ extern "C" int gof_accelerator(const float* d_pos_x, const float* d_pos_y, const
 extern "C" int gof_step1(float* vx, float* vy, float* vz, const float* ax, const float* ay, const float* az,
                          int n, float timestep, void* stream)
 {
+    DeviceGuard guard(device_of(vx));  // the arrays' device, whatever the caller's current one
     if (n <= 0) return 0;
     if (!vx || !vy || !vz || !ax || !ay || !az) return fail(GOF_E_INVALID, "gof_step1: null pointer");
     GOF_LAUNCH(k_step1, cdiv(n, kEwThreads), kEwThreads, 0, (cudaStream_t)stream, vx, vy, vz, ax, ay, az, n, timestep);
@@ -718,6 +764,7 @@ extern "C" int gof_step2(float* px, float* py, float* pz, float* vx, float* vy, 
                          const float* ay, const float* az, const int32_t* tia, const int32_t* self_kind, int n,
                          float timestep, void* stream)
 {
+    DeviceGuard guard(device_of(px));  // the arrays' device, whatever the caller's current one
     if (n <= 0) return 0;
     if (!px || !py || !pz || !vx || !vy || !vz || !ax || !ay || !az || !tia || !self_kind)
         return fail(GOF_E_INVALID, "gof_step2: null pointer");
@@ -729,6 +776,7 @@ extern "C" int gof_step2(float* px, float* py, float* pz, float* vx, float* vy, 
 extern "C" int gof_boundary_condition(float* px, float* py, float* pz, float lx, float ly, float lz, int n,
                                       void* stream)
 {
+    DeviceGuard guard(device_of(px));  // the arrays' device, whatever the caller's current one
     if (n <= 0) return 0;
     if (!px || !py || !pz) return fail(GOF_E_INVALID, "gof_boundary_condition: null pointer");
     GOF_LAUNCH(k_boundary, cdiv(n, kEwThreads), kEwThreads, 0, (cudaStream_t)stream, px, py, pz, lx, ly, lz, n);
@@ -738,6 +786,7 @@ extern "C" int gof_boundary_condition(float* px, float* py, float* pz, float lx,
 extern "C" int gof_max_sq_speed(const float* vx, const float* vy, const float* vz, int n, float* d_out,
                                 void* stream)
 {
+    DeviceGuard guard(device_of(vx));  // the arrays' device, whatever the caller's current one
     cudaStream_t st = (cudaStream_t)stream;
     if (!d_out) return fail(GOF_E_INVALID, "gof_max_sq_speed: null output");
     GOF_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float), st));
@@ -905,7 +954,7 @@ extern "C" int gof_engine_create(gof_engine** out, int device, int num_particles
 extern "C" void gof_engine_destroy(gof_engine* e)
 {
     if (!e) return;
-    cudaSetDevice(e->device);
+    DeviceGuard guard(e->device);
     for (cudaEvent_t v : e->ev) cudaEventDestroy(v);
     for (auto& g : e->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -923,7 +972,7 @@ extern "C" int gof_engine_set_graph(gof_engine* e, int enable)
 extern "C" int gof_engine_timing(gof_engine* e, int enable)
 {
     if (!e) return fail(GOF_E_INVALID, "null engine");
-    GOF_CUDA(cudaSetDevice(e->device));
+    DeviceGuard guard(e->device);
     e->timing = enable != 0;
     e->ev_used = 0;
     return 0;
@@ -932,7 +981,7 @@ extern "C" int gof_engine_timing(gof_engine* e, int enable)
 extern "C" int gof_engine_force_time(gof_engine* e, float* total_ms, int* launches)
 {
     if (!e || !total_ms || !launches) return fail(GOF_E_INVALID, "gof_engine_force_time: null pointer");
-    GOF_CUDA(cudaSetDevice(e->device));
+    DeviceGuard guard(e->device);
     float sum = 0.f;
     for (int k = 0; k < e->ev_used; ++k) {
         float ms = 0.f;
@@ -952,7 +1001,7 @@ extern "C" int gof_engine_bind_arena(gof_engine* e, void* d_arena, size_t bytes)
     if (!e || !d_arena) return fail(GOF_E_INVALID, "gof_engine_bind_arena: null pointer");
     if (bytes < e->arena_bytes) return fail(GOF_E_NOMEM, "gof_engine_bind_arena: arena too small");
     if ((uintptr_t)d_arena % 256) return fail(GOF_E_INVALID, "gof_engine_bind_arena: arena must be 256-byte aligned");
-    GOF_CUDA(cudaSetDevice(e->device));
+    DeviceGuard guard(e->device);
     engine_layout(e, (char*)d_arena);
     e->arena_base = (char*)d_arena;
     e->p2p = gof_engine::P2P{};
@@ -970,7 +1019,7 @@ extern "C" int gof_engine_set_parameters(gof_engine* e, const double* pm_host, v
     e->species_dirty = true;
     ++e->generation;  // the kinds decide which kernel instantiation a step launches
     if (e->bound) {
-        GOF_CUDA(cudaSetDevice(e->device));
+        DeviceGuard guard(e->device);
         if (int rc = upload_species(e->species, e->dspecies, (cudaStream_t)stream)) return rc;
         e->species_dirty = false;
     }
@@ -982,7 +1031,6 @@ static int engine_ready(gof_engine* e, bool need_state)
     if (!e) return fail(GOF_E_INVALID, "null engine");
     if (!e->bound) return fail(GOF_E_STATE, "engine has no arena: call gof_engine_bind_arena first");
     if (need_state && !e->uploaded) return fail(GOF_E_STATE, "engine has no state: call gof_engine_upload first");
-    GOF_CUDA(cudaSetDevice(e->device));
     return 0;
 }
 
@@ -990,7 +1038,9 @@ extern "C" int gof_engine_upload(gof_engine* e, const float* px, const float* py
                                  const float* vx, const float* vy, const float* vz, const float* ax,
                                  const float* ay, const float* az, const int32_t* types, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, false)) return rc;
+    if (e->slab) return fail(GOF_E_STATE, "gof_engine_upload: a slab engine takes its particles through gof_slab_upload");
     if (!px || !py || !pz || !types) return fail(GOF_E_INVALID, "gof_engine_upload: positions and types are required");
     cudaStream_t st = (cudaStream_t)stream;
     const int n = e->capacity;
@@ -1142,10 +1192,13 @@ static int engine_capture_step(gof_engine* e, float timestep, int wrap_mode)
 
 extern "C" int gof_engine_step(gof_engine* e, int n_steps, float timestep, int wrap_mode, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
         return fail(GOF_E_INVALID, "gof_engine_step: bad wrap_mode");
     if (timestep == 0.0f || timestep != timestep) return fail(GOF_E_INVALID, "gof_engine_step: bad timestep");
+    if (e->slab) return fail(GOF_E_STATE, "gof_engine_step: a slab engine steps through the gof_slab_* phases");
+    if (timestep < 0) timestep = -1.0f;  // every negative value means "adaptive": one graph key
     cudaStream_t st = (cudaStream_t)stream;
     for (int s = 0; s < n_steps; ++s) {
         const bool timed = e->timing && e->ev_used < kMaxTimedLaunches;
@@ -1167,9 +1220,11 @@ extern "C" int gof_engine_step(gof_engine* e, int n_steps, float timestep, int w
 
 extern "C" int gof_engine_accelerate(gof_engine* e, int wrap_mode, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
         return fail(GOF_E_INVALID, "gof_engine_accelerate: bad wrap_mode");
+    if (e->slab) return fail(GOF_E_STATE, "gof_engine_accelerate: not available on a slab engine");
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = engine_bin(e, false, st)) return rc;
     ForceArgs a;
@@ -1182,6 +1237,7 @@ extern "C" int gof_engine_accelerate(gof_engine* e, int wrap_mode, void* stream)
 extern "C" int gof_engine_download(gof_engine* e, float* px, float* py, float* pz, float* vx, float* vy,
                                    float* vz, float* ax, float* ay, float* az, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = e->n;
@@ -1197,6 +1253,7 @@ extern "C" int gof_engine_download(gof_engine* e, float* px, float* py, float* p
 
 extern "C" int gof_engine_snapshot(gof_engine* e, float* xyz, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     if (!xyz) return fail(GOF_E_INVALID, "gof_engine_snapshot: null output");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1213,6 +1270,7 @@ extern "C" int gof_engine_snapshot(gof_engine* e, float* xyz, void* stream)
  * next `stage` must wait for the previous `copy`. */
 extern "C" int gof_engine_snapshot_stage(gof_engine* e, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     const int n = e->n;
     GOF_LAUNCH(k_snapshot, cdiv(n, kEwThreads), kEwThreads, 0, (cudaStream_t)stream, e->posw[0], e->veli[0], n,
@@ -1222,6 +1280,7 @@ extern "C" int gof_engine_snapshot_stage(gof_engine* e, void* stream)
 
 extern "C" int gof_engine_snapshot_copy(gof_engine* e, float* xyz, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     if (!xyz) return fail(GOF_E_INVALID, "gof_engine_snapshot_copy: null output");
     GOF_CUDA(cudaMemcpyAsync(xyz, e->stage_xyz, (size_t)e->n * 3 * sizeof(float), cudaMemcpyDefault,
@@ -1232,6 +1291,7 @@ extern "C" int gof_engine_snapshot_copy(gof_engine* e, float* xyz, void* stream)
 extern "C" int gof_engine_read_bins(gof_engine* e, int32_t* particle_bins, int32_t* bin_counts,
                                     int32_t* bin_starts, int32_t* particle_indices, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     if (!e->binned) return fail(GOF_E_STATE, "gof_engine_read_bins: no step or accelerate has run since the upload");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1253,6 +1313,7 @@ extern "C" int gof_engine_read_bins(gof_engine* e, int32_t* particle_bins, int32
  * Synchronises `stream`. */
 extern "C" int gof_engine_pair_stats(gof_engine* e, int wrap_mode, unsigned long long* out3, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     if (!out3) return fail(GOF_E_INVALID, "gof_engine_pair_stats: null output");
     if (!e->binned) return fail(GOF_E_STATE, "gof_engine_pair_stats: no step or accelerate has run since the upload");
@@ -1273,6 +1334,7 @@ extern "C" int gof_engine_pair_stats(gof_engine* e, int wrap_mode, unsigned long
 
 extern "C" int gof_engine_last_timestep(gof_engine* e, float* out, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = engine_ready(e, true)) return rc;
     if (!out) return fail(GOF_E_INVALID, "gof_engine_last_timestep: null output");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1370,6 +1432,7 @@ extern "C" int gof_slab_upload(gof_engine* e, int n, const float* px, const floa
                                const float* ay, const float* az, const int32_t* types, const int32_t* ids,
                                void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, false)) return rc;
     if (n < 0 || n > e->capacity) return fail(GOF_E_NOMEM, "gof_slab_upload: more particles than capacity");
     if (n > 0 && (!px || !py || !pz || !types || !ids)) return fail(GOF_E_INVALID, "gof_slab_upload: null pointer");
@@ -1406,6 +1469,7 @@ extern "C" int gof_slab_upload(gof_engine* e, int n, const float* px, const floa
 /* Device pointers the host wraps as tensors for send/recv (all inside the bound arena). */
 extern "C" int gof_slab_pointers(gof_engine* e, void** ptrs, int n_ptrs)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, false)) return rc;
     if (!ptrs || n_ptrs < 11) return fail(GOF_E_INVALID, "gof_slab_pointers: need room for 11 pointers");
     ptrs[0] = e->mig_send[0];
@@ -1439,6 +1503,7 @@ __global__ void k_slab_counts(const int* __restrict__ start, const int* __restri
  * whole (fixed size) and phase 2 reads the counts on the device. */
 extern "C" int gof_slab_phase_hash_async(gof_engine* e, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, true)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const Geometry& g = e->geom;
@@ -1463,23 +1528,27 @@ extern "C" int gof_slab_phase_hash_async(gof_engine* e, void* stream)
  * all-gathers them and reports them back with gof_slab_commit. */
 extern "C" int gof_slab_phase_sort_async(gof_engine* e, float timestep, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, true)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const Geometry& g = e->geom;
     const int max_arrivals = 2 * e->mig_capacity;
     int bound = e->n_slots + max_arrivals;  // slots that may be in use after the append
     if (bound > e->capacity) bound = e->capacity;
-    if (e->n_slots + 64 > e->capacity) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
-    const int room = bound - e->n_slots;
+    // (no room left for arrivals: a device flag, so that it travels with the words every rank
+    // gathers and all of them raise, instead of one rank failing here while its peers wait)
+    if (e->n_slots + 64 > e->capacity) GOF_LAUNCH(k_set_word, 1, 1, 0, st, e->counters + 2, 5);
+    const int room = bound - e->n_slots > 0 ? bound - e->n_slots : 0;
     int* words = e->counters;  // [0] arrivals, [1] slots in use ([2] is the error flag)
     GOF_LAUNCH(k_append_arrivals, cdiv(max_arrivals, kBinThreads), kBinThreads, 0, st, e->mig_recv[0], e->mig_recv[1],
                e->mig_capacity < room / 2 ? e->mig_capacity : room / 2, e->n_slots, e->posw[0], e->veli[0], e->acc,
                words);
     MigrateOut flag_only{nullptr, nullptr, e->counters + 2, 0};
-    GOF_LAUNCH(k_hash_count<false>, cdiv(room, kBinThreads), kBinThreads, 0, st, e->posw[0] + e->n_slots,
-               e->veli[0] + e->n_slots, e->acc + e->n_slots, (const float*)nullptr, (const float*)nullptr,
-               (const float*)nullptr, room, (const int*)words, g, e->cell_of + e->n_slots, e->off + e->n_slots,
-               e->count, flag_only);
+    if (room > 0)
+        GOF_LAUNCH(k_hash_count<false>, cdiv(room, kBinThreads), kBinThreads, 0, st, e->posw[0] + e->n_slots,
+                   e->veli[0] + e->n_slots, e->acc + e->n_slots, (const float*)nullptr, (const float*)nullptr,
+                   (const float*)nullptr, room, (const int*)words, g, e->cell_of + e->n_slots, e->off + e->n_slots,
+                   e->count, flag_only);
     GOF_LAUNCH(k_prepare_dt, 1, 1, 0, st, e->scalars, e->parity, timestep < 0 ? -1.0f : timestep);
     if (int rc = launch_scan(e->count, g.num_cells + 1, e->tile_sums, e->start, st)) return rc;
     GOF_LAUNCH(k_scatter_ids<false>, cdiv(bound, kBinThreads), kBinThreads, 0, st, e->veli[0], bound,
@@ -1498,9 +1567,11 @@ extern "C" int gof_slab_phase_sort_async(gof_engine* e, float timestep, void* st
 /* The host's copy of counters[4..7] after phase 2 (it needs them for the halo messages anyway). */
 extern "C" int gof_slab_commit(gof_engine* e, int n_live, int lo_pop, int hi_pop, int error)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, true)) return rc;
     if (error == 1) return fail(GOF_E_STATE, "slab: a particle moved more than one layer in a step, or arrived in the wrong slab");
     if (error == 2) return fail(GOF_E_NOMEM, "slab: migration buffer overflow (raise migrate_capacity)");
+    if (error == 5) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
     if (n_live < 0 || n_live > e->capacity) return fail(GOF_E_NOMEM, "slab: particle capacity exceeded");
     if (lo_pop > e->halo_capacity || hi_pop > e->halo_capacity)
         return fail(GOF_E_NOMEM, "slab: boundary layer larger than halo_capacity");
@@ -1535,6 +1606,7 @@ static int slab_timed_force(gof_engine* e, const ForceArgs& a, cudaStream_t st)
  * read from the device words of phase 2. */
 extern "C" int gof_slab_phase_force_interior(gof_engine* e, int wrap_mode, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, true)) return rc;
     if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
         return fail(GOF_E_INVALID, "gof_slab_phase_force_interior: bad wrap_mode");
@@ -1589,6 +1661,7 @@ static int slab_force_boundary(gof_engine* e, int n_halo_lo, int n_halo_hi, int 
 extern "C" int gof_slab_phase_force_boundary(gof_engine* e, int n_halo_lo, int n_halo_hi, int wrap_mode,
                                              void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, true)) return rc;
     return slab_force_boundary(e, n_halo_lo, n_halo_hi, wrap_mode, false, (cudaStream_t)stream);
 }
@@ -1596,6 +1669,7 @@ extern "C" int gof_slab_phase_force_boundary(gof_engine* e, int n_halo_lo, int n
 /* Phase 3 in one call (no overlap): halo table + all owned particles. */
 extern "C" int gof_slab_phase_force(gof_engine* e, int n_halo_lo, int n_halo_hi, int wrap_mode, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, true)) return rc;
     return slab_force_boundary(e, n_halo_lo, n_halo_hi, wrap_mode, true, (cudaStream_t)stream);
 }
@@ -1634,6 +1708,7 @@ static int slab_p2p_sync_count(gof_engine* e, cudaStream_t st)
 
 extern "C" int gof_slab_check(gof_engine* e, int* n_live, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, true)) return rc;
     if (int rc = slab_p2p_sync_count(e, (cudaStream_t)stream)) return rc;
     if (n_live) *n_live = e->n;
@@ -1642,6 +1717,7 @@ extern "C" int gof_slab_check(gof_engine* e, int* n_live, void* stream)
 
 extern "C" int gof_slab_window(gof_engine* e, int64_t* info, int n_info)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, false)) return rc;
     if (!info || n_info < 12) return fail(GOF_E_INVALID, "gof_slab_window: need room for 12 words");
     auto off = [&](const void* p) { return (int64_t)((const char*)p - e->arena_base); };
@@ -1662,6 +1738,7 @@ extern "C" int gof_slab_window(gof_engine* e, int64_t* info, int n_info)
 
 extern "C" int gof_slab_connect(gof_engine* e, int rank, int world, void* const* bases, const int64_t* infos)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, false)) return rc;
     if (!bases || !infos || world < 2 || world > kMaxWorld || rank < 0 || rank >= world)
         return fail(GOF_E_INVALID, "gof_slab_connect: bad arguments (2 <= world <= 16)");
@@ -1724,7 +1801,11 @@ extern "C" int gof_slab_connect(gof_engine* e, int rank, int world, void* const*
 extern "C" int gof_slab_step_p2p(gof_engine* const* slabs, int n_slabs, int n_steps, float timestep, int wrap_mode,
                                  void* main_stream, void* side_stream)
 {
-    if (!slabs || n_slabs < 1) return fail(GOF_E_INVALID, "gof_slab_step_p2p: no slabs");
+    if (!slabs || n_slabs < 1 || !slabs[0]) return fail(GOF_E_INVALID, "gof_slab_step_p2p: no slabs");
+    DeviceGuard guard(slabs[0]->device);  // (the slabs of one call share a device and its two streams)
+    for (int s = 1; s < n_slabs; ++s)
+        if (!slabs[s] || slabs[s]->device != slabs[0]->device)
+            return fail(GOF_E_INVALID, "gof_slab_step_p2p: the slabs of one call must live on one device");
     if (wrap_mode != GOF_WRAP_REFERENCE && wrap_mode != GOF_WRAP_MINIMAGE)
         return fail(GOF_E_INVALID, "gof_slab_step_p2p: bad wrap_mode");
     if (timestep == 0.0f || timestep != timestep) return fail(GOF_E_INVALID, "gof_slab_step_p2p: bad timestep");
@@ -1898,6 +1979,7 @@ extern "C" int gof_slab_count(const gof_engine* e) { return e ? e->n : 0; }
 extern "C" int gof_slab_download(gof_engine* e, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
                                  float* ax, float* ay, float* az, int32_t* ids, int32_t* types, void* stream)
 {
+    DeviceGuard guard(e ? e->device : -1);
     if (int rc = slab_ready(e, true)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (e->p2p.on)

@@ -78,6 +78,7 @@ struct ForceArgs {
     float* boid_vel_x; float* boid_vel_y; float* boid_vel_z;
     int n_total;
     int slot_limit;           // upper bound of the indices into posw / veli (Boids-kind queue entries)
+    int wave_sms;             // SMs of the device (placement of the literal z-wrap blocks in the first wave)
 };
 
 // Per-thread state of the particle being updated.
@@ -1140,7 +1141,8 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
         int r = p;
         // The first wave (kWaveSMs x kWaveBlocks launch indices, handed out round-robin over the SMs)
         // gives the literal blocks to the first W SMs only, so that the two hot loops do not share an SM.
-        constexpr int kWaveSMs = 148, kWaveBlocks = SPLIT == 1 ? GOF_FORCE_MINBLOCKS : 2;
+        constexpr int kWaveBlocks = SPLIT == 1 ? GOF_FORCE_MINBLOCKS : 2;
+        const int kWaveSMs = a.wave_sms;
         const int W = (nq + kWaveBlocks - 1) / kWaveBlocks;
         if (W <= kWaveSMs && grid >= kWaveSMs * kWaveBlocks) {
             if (p < kWaveSMs * kWaveBlocks) {

@@ -402,6 +402,18 @@ class SlabRunner:
         self.world_slabs = int(world_slabs)
         self.comm = comm
         self.messages = 0                 # tensors handed to the transport so far (diagnostics)
+        self.transport = "copies / send-recv sequenced from Python, sizes gathered per step"
+        # Capacities are part of the protocol: every rank must be able to check EVERY slab's words
+        # (a sender can pass its own check with a layer its receiver cannot hold), so they are
+        # gathered once here: {slab: [capacity, halo_capacity, migrate_capacity, 0]}.
+        dev = next(iter(self.slabs.values())).device if self.slabs and hasattr(next(iter(self.slabs.values())), "device") else None
+        mk = lambda e: torch.tensor([int(getattr(e, "capacity", 1 << 30)), int(getattr(e, "halo_capacity", 1 << 30)),
+                                     int(getattr(e, "migrate_capacity", 0)), 0], dtype=torch.int32,
+                                    device=dev if dev is not None else "cpu")
+        self.caps = self.comm.gather_words({s: mk(e) for s, e in self.slabs.items()})
+        migs = {c[2] for c in self.caps.values()}
+        if len(migs) > 1:
+            raise ValueError(f"SlabRunner: migrate_capacity must be the same on every slab, got {sorted(migs)}")
         # GOF_SLAB_TIMING=1: device time of the serial part of a step (hash + migration + sort) and
         # of the forces (with the halo traffic underneath), summed over the steps, in `phase_ms`
         self.phase_ms = {"prefix": 0.0, "forces": 0.0, "steps": 0} if os.environ.get("GOF_SLAB_TIMING") else None
@@ -453,6 +465,9 @@ class SlabRunner:
                 for e in self.slabs.values():
                     e.phase_force_interior()
                 first = next(iter(self.slabs.values()))
+                # one side stream: the local slabs of a runner share a device (asserted below)
+                assert all(e.index == first.index for e in self.slabs.values()), \
+                    "SlabRunner(overlap=True): the slabs of one process must live on one device"
                 side = first.side_stream()
                 for s in self.slabs:
                     side.wait_event(sorted_ev[s])
@@ -461,6 +476,9 @@ class SlabRunner:
                 ctx = contextlib.nullcontext()
             with ctx:
                 pops = self.comm.gather_words({s: e.sort_words() for s, e in self.slabs.items()})
+                # Every rank looks at EVERY slab's words and raises the same error, before any halo
+                # byte moves: a failure seen by one rank only would leave its peers in send/recv.
+                self._check_words(pops)
                 for s, e in self.slabs.items():
                     e.commit(pops[s])
                 transfers = []
@@ -498,6 +516,27 @@ class SlabRunner:
                 self.phase_ms["prefix"] += marks[0].elapsed_time(marks[1])
                 self.phase_ms["forces"] += marks[1].elapsed_time(marks[2])
                 self.phase_ms["steps"] += 1
+
+    _ERRORS = {1: "a particle moved more than one layer in a step, or arrived in the wrong slab",
+               2: "migration buffer overflow (raise migrate_capacity)",
+               5: "particle capacity exceeded"}
+
+    def _check_words(self, pops):
+        """pops: {slab: [live, bottom layer, top layer, error]} of ALL slabs (identical on every rank)."""
+        for s in range(self.world_slabs):
+            live, lo, hi, err = pops[s]
+            if err:
+                raise _lib.GofError(_lib.E_STATE if err == 1 else _lib.E_NOMEM,
+                                    f"slab {s}: {self._ERRORS.get(err, f'device-side error {err}')}")
+            if live > self.caps[s][0]:
+                raise _lib.GofError(_lib.E_NOMEM, f"slab {s}: particle capacity exceeded ({live} > {self.caps[s][0]})")
+            below, above = self._below(s), self._above(s)
+            if lo > self.caps[below][1]:
+                raise _lib.GofError(_lib.E_NOMEM, f"slab {s}: bottom layer of {lo} particles does not fit slab {below}'s "
+                                                  f"halo_capacity {self.caps[below][1]}")
+            if hi > self.caps[above][1]:
+                raise _lib.GofError(_lib.E_NOMEM, f"slab {s}: top layer of {hi} particles does not fit slab {above}'s "
+                                                  f"halo_capacity {self.caps[above][1]}")
 
     def close(self):
         pass

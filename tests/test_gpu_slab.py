@@ -101,3 +101,44 @@ def test_p2p_slab_errors_surface_on_the_host():
     runner.close()
     for e in slabs.values():
         e.close()
+
+
+def test_migration_overflow_raises_on_the_sequenced_transport():
+    """The same overflow on the Python-sequenced transport (send/recv, here device copies): the
+    sticky flag travels in the gathered words and the size check raises before the halo exchange."""
+    from game_of_flies_b200 import _lib
+    from game_of_flies_b200.slab import LocalComm, SlabEngine, SlabRunner, assign_to_slabs, split_layers
+    st = random_state([6000] * 3, (100, 100, 200), seed=5, kinds="clusters", speed=15.0)
+    grid = orc.grid_from_limits(st["limits"], st["r_max"])
+    layers = split_layers(grid["num_bin_z"], 2)
+    owner = assign_to_slabs(st["pos"][2], grid["bin_size_z"], grid["num_bin_z"], layers)
+    slabs = {}
+    for s, (lo, hi) in enumerate(layers):
+        m = owner == s
+        e = SlabEngine(st["parameter_matrix"], st["limits"], st["r_max"], lo, hi, capacity=int(m.sum() * 1.5) + 4096,
+                       migrate_capacity=2)
+        e.upload(st["pos"][:, m], st["types"][m], np.nonzero(m)[0], vel=st["vel"][:, m], acc=st["acc"][:, m])
+        slabs[s] = e
+    runner = SlabRunner(slabs, 2, LocalComm(2))
+    with pytest.raises(_lib.GofError, match="migration buffer overflow"):
+        runner.step(30, 0.05)
+    for e in slabs.values():
+        e.close()
+
+
+def test_engine_entry_points_reject_slab_engines():
+    """gof_engine_step / accelerate / upload on an engine made by gof_slab_create must fail instead
+    of treating the local slab grid as a whole periodic box."""
+    import ctypes as C
+    import torch
+    from game_of_flies_b200 import _lib
+    from game_of_flies_b200.slab import SlabEngine
+    st = random_state([2000] * 2, (80, 80, 160), seed=3, kinds="clusters")
+    e = SlabEngine(st["parameter_matrix"], st["limits"], st["r_max"], 0, 4, capacity=8192)
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.gof_engine_step(e._handle, 1, C.c_float(-1.0), 0, stream) == _lib.E_STATE
+    assert lib.gof_engine_accelerate(e._handle, 0, stream) == _lib.E_STATE
+    # the caller's current device is left alone by every entry point
+    assert torch.cuda.current_device() == e.index
+    e.close()

@@ -108,3 +108,61 @@ def test_two_gloo_ranks_follow_the_oracle(timestep):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(2, port, timestep, ret), nprocs=2, join=True)
     assert len(ret) == 2 and sum(ret.values()) == make_state()["n"]
+
+
+def test_word_checks_raise_on_every_slabs_failure():
+    """After the size all-gather every rank inspects EVERY slab's words: an error flag, a live
+    count over capacity or a boundary layer the RECEIVER cannot hold raises the same error
+    everywhere (a rank that only checked its own slab would leave its peers in send/recv)."""
+    from game_of_flies_b200 import _lib
+    st = make_state()
+    slabs = build_slabs(st, 3, range(3))
+    for s, e in slabs.items():
+        e.capacity, e.halo_capacity, e.migrate_capacity = 1000, 50 + 10 * s, 64
+    runner = SlabRunner(slabs, 3, LocalComm(3))
+    assert runner.caps == {0: [1000, 50, 64, 0], 1: [1000, 60, 64, 0], 2: [1000, 70, 64, 0]}
+    ok = {0: [100, 40, 40, 0], 1: [100, 40, 40, 0], 2: [100, 40, 40, 0]}
+    runner._check_words(ok)
+    with pytest.raises(_lib.GofError, match="slab 1: migration buffer overflow"):
+        runner._check_words({**ok, 1: [100, 40, 40, 2]})
+    with pytest.raises(_lib.GofError, match="slab 2: particle capacity exceeded"):
+        runner._check_words({**ok, 2: [1001, 40, 40, 0]})
+    # slab 1's bottom layer goes to slab 0 (halo_capacity 50): 55 does not fit although slab 1 could hold it
+    with pytest.raises(_lib.GofError, match="slab 1: bottom layer of 55 particles does not fit slab 0"):
+        runner._check_words({**ok, 1: [100, 55, 40, 0]})
+    slabs[2].migrate_capacity = 128
+    with pytest.raises(ValueError, match="migrate_capacity must be the same"):
+        SlabRunner(slabs, 3, LocalComm(3))
+
+
+def _worker_error(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    from game_of_flies_b200 import _lib
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        st = make_state()
+        slabs = build_slabs(st, world, [rank])
+        for e in slabs.values():
+            e.capacity, e.migrate_capacity = 10_000, 64
+            e.halo_capacity = 10_000 if rank == 0 else 3   # rank 1 cannot hold rank 0's boundary layers
+        runner = SlabRunner(slabs, world, DistComm(world))
+        try:
+            runner.step(1, 0.05)
+            ret[rank] = "no error"
+        except _lib.GofError as exc:
+            ret[rank] = str(exc)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_raise_the_same_error():
+    """The failure belongs to rank 0's layers and rank 1's capacity: both ranks must raise, and
+    neither may be left waiting in an exchange."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_error, args=(2, port, ret), nprocs=2, join=True)
+    assert len(ret) == 2 and ret[0] == ret[1] and "does not fit slab 1's halo_capacity 3" in ret[0], dict(ret)
