@@ -330,6 +330,7 @@ static size_t force_smem_bytes(int T, int kind, int split)
     return (size_t)T * T * sizeof(PairParam) + (size_t)T * kRowBytes +
            (kind != kKindClusters ? (size_t)T * kBoidSlots * kForceThreads * sizeof(float) : 0) +
            (kind == kKindBoids ? (size_t)kQueueDepth * kForceThreads * sizeof(unsigned) : 0) +
+           (kind == kKindMixed ? (size_t)(kForceThreads / 32) * kListLen * 2 * sizeof(float4) : 0) +
            (split > 1 ? (size_t)kSplitRuns * 3 * kSplitHomes * sizeof(float) : 0) +
            (kind == kKindClusters ? (size_t)(split > 1 ? split : kForceThreads / 32) * kListLen * (sizeof(float4) + sizeof(int)) : 0);
 }
@@ -1324,7 +1325,7 @@ extern "C" int gof_engine_pair_stats(gof_engine* e, int wrap_mode, unsigned long
     GOF_CUDA(cudaMemsetAsync(d, 0, sizeof(PairStats), st));
     GOF_LAUNCH(k_pair_stats, cdiv(e->n, kForceThreads), kForceThreads, 0, st, e->geom, (const float4*)e->posw[1],
                (const int*)e->cell_sorted, (const int*)e->start, (const int*)e->count, e->n, wrap_mode,
-               e->species.kind() == kKindClusters ? 1 : 0, d);
+               e->species.kind() != kKindBoids ? 1 : 0, d);  // (the Clusters and the mixed kind cull per warp)
     PairStats hst{};
     GOF_CUDA(cudaMemcpyAsync(&hst, d, sizeof(PairStats), cudaMemcpyDeviceToHost, st));
     GOF_CUDA(cudaStreamSynchronize(st));

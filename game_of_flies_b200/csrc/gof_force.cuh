@@ -28,7 +28,15 @@
 namespace gof {
 
 constexpr int kForceThreads = 128;
-constexpr int kBoidSlots = 7;  // per partner type: count, sum of relative positions (3), sum of velocities (3)
+constexpr int kBoidSlots = 8;  // per partner type, two float4: {count, sum of relative positions}, {sum of velocities, -}
+
+// The per-type sums of a thread live in shared memory as float4 pairs: vector v (0 / 1) of partner
+// type t sits (t * 2 + v) * kForceThreads float4 behind the thread's first one, so that a warp's
+// 16-byte accesses are contiguous (conflict-free) and one pair's update is two loads + two stores.
+__device__ __forceinline__ float4* boid_vec(float* boid_acc, int t, int v)
+{
+    return reinterpret_cast<float4*>(boid_acc) + (t * 2 + v) * kForceThreads;
+}
 
 // which kinds of species pairs a launch has to handle (decides the code of the hot loop)
 enum ForceKind : int {
@@ -130,7 +138,7 @@ template <typename ExactD2>
 __device__ __forceinline__ void interact_boids(Home& h, const float4 qa, float* __restrict__ boid_acc,
                                                const ForceArgs& a, int T, int j, int tj, float dx, float dy,
                                                float dz, float rx, float ry, float rz, float inv, float dist,
-                                               ExactD2 exact_d2)
+                                               ExactD2 exact_d2, const float4* vj_known = nullptr)
 {
     bool sep = dist < qa.x;
     if (fabsf(dist - qa.x) < 4e-6f * qa.x) {
@@ -143,22 +151,22 @@ __device__ __forceinline__ void interact_boids(Home& h, const float4 qa, float* 
         h.ay = fmaf(s, dy, h.ay);
         h.az = fmaf(s, dz, h.az);
     }
-    const float4 vj = ldg4(a.veli + j);
-    float* slot = boid_acc + tj * kBoidSlots * kForceThreads;
-    slot[0 * kForceThreads] += 1.0f;
-    slot[1 * kForceThreads] += rx;
-    slot[2 * kForceThreads] += ry;
-    slot[3 * kForceThreads] += rz;
-    slot[4 * kForceThreads] += vj.x;
-    slot[5 * kForceThreads] += vj.y;
-    slot[6 * kForceThreads] += vj.z;
+    const float4 vj = vj_known ? *vj_known : ldg4(a.veli + j);
+    float4* s0 = boid_vec(boid_acc, tj, 0);
+    float4* s1 = boid_vec(boid_acc, tj, 1);
+    float4 c = *s0, v = *s1;
+    c.x += 1.0f; c.y += rx; c.z += ry; c.w += rz;
+    v.x += vj.x; v.y += vj.y; v.z += vj.z;
+    *s0 = c;
+    *s1 = v;
 }
 
 template <bool BOIDS, typename ExactD2>
 __device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ tabrow,
                                          float* __restrict__ boid_acc, const ForceArgs& a,
                                          int T, int j, int tj, float dx, float dy, float dz,
-                                         float rx, float ry, float rz, float d2, ExactD2 exact_d2)
+                                         float rx, float ry, float rz, float d2, ExactD2 exact_d2,
+                                         const float4* vj_known = nullptr)
 {
     const float inv = fast_rsqrt(d2);
     const float dist = d2 * inv;
@@ -173,7 +181,7 @@ __device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ 
         h.ay = fmaf(-s, dy, h.ay);
         h.az = fmaf(-s, dz, h.az);
     } else {
-        interact_boids(h, qa, boid_acc, a, T, j, tj, dx, dy, dz, rx, ry, rz, inv, dist, exact_d2);
+        interact_boids(h, qa, boid_acc, a, T, j, tj, dx, dy, dz, rx, ry, rz, inv, dist, exact_d2, vj_known);
     }
 }
 
@@ -693,6 +701,220 @@ __device__ __forceinline__ void walk_image(Home& h, RowAddr tabrow_s, const Pair
         walk_culled<false, false>(h, tabrow_s, tabrow, a, g, im, b, sx, sy, sz, s, e, lst, 0u, 0);
 }
 
+// ---- mixed systems (Clusters- and Boids-kind pairs): the whole-warp walk, one unified pair ------
+// The per-lane walk (pair_branchy) runs the interaction behind a branch with the few lanes that
+// have this candidate in range (15 of 32 on average), and a Boids-kind pair costs seven
+// shared-memory read-modify-writes.  When the 32 home particles of a warp share a row of cells the
+// warp walks the union of their runs as one, like the Clusters kind (walk_culled): candidates are
+// culled against the box of the 32, the survivors' positions AND velocities go to two lists, and
+// every lane evaluates every survivor BRANCH-FREE: both force laws computed, one selected by the
+// kind of the species pair and the cut-off, the Boids sums multiplied by a 0 / 1 mask.  All lanes
+// see the same candidate at the same time, so its type is warp-uniform: the seven running sums of
+// the partner type the walk is in stay in registers and are exchanged with their shared-memory
+// slot (two 16-byte loads, two stores) only when the type changes.  The sums still grow pair by
+// pair in candidate order
+// (slot -> registers -> slot moves nothing), and a masked-out pair adds exactly zero, so a
+// particle's result equals that of the per-lane walk bit for bit.  The float64 decisions (guard
+// band of r_max^2, edge of the separation radius) are rare: a block of four survivors in which
+// some lane needs one is redone by the per-lane code, pair by pair.
+struct BoidRun {
+    float c, rx, ry, rz, vx, vy, vz;  // count, sum of relative positions, sum of velocities
+    int t;                             // partner type they belong to (-1: nothing in registers)
+};
+
+__device__ __forceinline__ void boidrun_store(BoidRun& r, float* __restrict__ boid_acc)
+{
+    if (r.t < 0) return;
+    *boid_vec(boid_acc, r.t, 0) = make_float4(r.c, r.rx, r.ry, r.rz);
+    *boid_vec(boid_acc, r.t, 1) = make_float4(r.vx, r.vy, r.vz, 0.0f);
+    r.t = -1;
+}
+
+__device__ __forceinline__ void boidrun_load(BoidRun& r, const float* __restrict__ boid_acc, int t)
+{
+    const float4 c = *boid_vec(const_cast<float*>(boid_acc), t, 0), v = *boid_vec(const_cast<float*>(boid_acc), t, 1);
+    r.c = c.x; r.rx = c.y; r.ry = c.z; r.rz = c.w;
+    r.vx = v.x; r.vy = v.y; r.vz = v.z;
+    r.t = t;
+}
+
+// One survivor, every lane, no branch.  Returns true when this lane needs a float64 decision for
+// it (the caller then redoes the whole block with the per-lane code; nothing of this call counts).
+struct MixedPair { float s, m, dx, dy, dz; bool exact; };
+
+// The parameter rows of a mixed system are laid out so that ONE formula serves both kinds
+// (k_force's prologue): a Boids-kind pair stores A = {r_sep, 0, -separation, 0}, B = {0, 0, 1, 1 / r_sep^2}
+// -- the Clusters profile then yields -separation inside r_sep and 0 outside, i.e. exactly the
+// Boids separation term once negated like every Clusters force -- and a Clusters-kind pair
+// B = {s1, f_max, 0, 0}: B.z is the 0 / 1 mask of the Boids sums, B.w = 1 / r_sep^2 marks the
+// separation radius whose edge needs a float64 decision (never matched when 0).
+template <bool LOWFIX>
+__device__ __forceinline__ MixedPair pair_mixed(RowAddr tabrow_s, const Geometry& g, const Image& im, const float4 pj)
+{
+    MixedPair r;
+    float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
+    if (LOWFIX) { dx += im.lx; dy += im.ly; dz += im.lz; }
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const unsigned at = tabrow_s.a + ((unsigned)__float_as_int(pj.w) << 4);
+    const float4 qa = lds4(at);
+    const float4 qb = lds4(at + kRowB);
+    const float inv = fast_rsqrt(d2);
+    const float dist = d2 * inv;
+    const bool below = d2 < g.r2_lo;
+    const bool in = below && d2 > 1e-10f;
+    const float f_in = fmaf(-qa.y, dist, qa.z);
+    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
+    const float sc = (dist < qa.x ? f_in : f_tri) * -inv;  // already negated: a += sc * d
+    r.s = in ? sc : 0.0f;
+    r.m = in ? qb.z : 0.0f;
+    r.dx = dx; r.dy = dy; r.dz = dz;
+    // float64 decisions: the guard band of r_max^2, and -- in squared distances, a little wider than
+    // the per-lane code's |dist - r_sep| < 4e-6 r_sep -- the edge of the separation radius
+    r.exact = (!below && d2 < g.r2_hi) || fabsf(fmaf(d2, qb.w, -1.0f)) < 1e-5f;
+    return r;
+}
+
+__device__ __forceinline__ void apply_mixed(Home& h, BoidRun& run, const MixedPair& r, const float4 vj)
+{
+    h.ax = fmaf(r.s, r.dx, h.ax);
+    h.ay = fmaf(r.s, r.dy, h.ay);
+    h.az = fmaf(r.s, r.dz, h.az);
+    run.c += r.m;
+    run.rx = fmaf(r.m, -r.dx, run.rx);
+    run.ry = fmaf(r.m, -r.dy, run.ry);
+    run.rz = fmaf(r.m, -r.dz, run.rz);
+    run.vx = fmaf(r.m, vj.x, run.vx);
+    run.vy = fmaf(r.m, vj.y, run.vy);
+    run.vz = fmaf(r.m, vj.z, run.vz);
+}
+
+// four survivors from the warp's lists (positions at `at`, velocities at `at_v`)
+template <bool LOWFIX>
+__device__ __forceinline__ void walk_group_mixed(Home& h, BoidRun& run, RowAddr tabrow_s,
+                                                 const PairParam* __restrict__ tabrow, float* __restrict__ boid_acc,
+                                                 const ForceArgs& a, const Geometry& g, const Image& im, unsigned at,
+                                                 unsigned at_v)
+{
+    const float4 p0 = lds4v(at), p1 = lds4v(at + 16u), p2 = lds4v(at + 32u), p3 = lds4v(at + 48u);
+    const MixedPair r0 = pair_mixed<LOWFIX>(tabrow_s, g, im, p0), r1 = pair_mixed<LOWFIX>(tabrow_s, g, im, p1),
+                    r2 = pair_mixed<LOWFIX>(tabrow_s, g, im, p2), r3 = pair_mixed<LOWFIX>(tabrow_s, g, im, p3);
+    if (!__any_sync(0xffffffffu, r0.exact | r1.exact | r2.exact | r3.exact)) {
+        const float4 v0 = lds4v(at_v), v1 = lds4v(at_v + 16u), v2 = lds4v(at_v + 32u), v3 = lds4v(at_v + 48u);
+        // the candidate's type is the same in every lane: a warp-uniform exchange of the running sums
+        int t = __float_as_int(p0.w);
+        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+        apply_mixed(h, run, r0, v0);
+        t = __float_as_int(p1.w);
+        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+        apply_mixed(h, run, r1, v1);
+        t = __float_as_int(p2.w);
+        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+        apply_mixed(h, run, r2, v2);
+        t = __float_as_int(p3.w);
+        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+        apply_mixed(h, run, r3, v3);
+        return;
+    }
+    // some lane needs a float64 decision in this block: the per-lane code for all four, on the
+    // shared-memory slots (out of line: ~1 block in 1000)
+    boidrun_store(run, boid_acc);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const float4 pj = lds4v(at + 16u * k), vj = lds4v(at_v + 16u * k);
+        float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
+        if (LOWFIX) { dx += im.lx; dy += im.ly; dz += im.lz; }
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d2 < g.r2_hi && d2 > 1e-10f) {
+            bool ok = true;
+            if (d2 > g.r2_lo) {
+                const double e = exact_dist2(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts);
+                ok = (1e-10 < e) && (e < g.r2d);
+            }
+            if (ok)
+                interact<true>(h, tabrow, boid_acc, a, a.T, 0, __float_as_int(pj.w), dx, dy, dz, -dx, -dy, -dz, d2,
+                               [&]() { return exact_dist2(g, h.x, h.y, h.z, pj.x, pj.y, pj.z, im.shifts); }, &vj);
+        }
+    }
+}
+
+// like walk_culled (not LITERAL): `lst` / `lst_v` = the warp's survivor lists (kListLen float4 each)
+template <bool LOWFIX>
+__device__ __forceinline__ void walk_culled_mixed(Home& h, BoidRun& run, RowAddr tabrow_s,
+                                                  const PairParam* __restrict__ tabrow, float* __restrict__ boid_acc,
+                                                  const ForceArgs& a, const Geometry& g, const Image& im, const Box& b,
+                                                  int sx, int sy, int sz, int s, int e, unsigned lst, unsigned lst_v)
+{
+    // the run sums into its own accumulator, like run_pairs
+    const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+    h.ax = h.ay = h.az = 0.0f;
+    const float tx = sx * g.Lx, ty = sy * g.Ly, tz = sz * g.Lz;
+    const float lox = b.lox + tx - g.cull_slack, hix = b.hix + tx + g.cull_slack;
+    const float loy = b.loy + ty - g.cull_slack, hiy = b.hiy + ty + g.cull_slack;
+    const float loz = b.loz + tz - g.cull_slack, hiz = b.hiz + tz + g.cull_slack;
+    const unsigned lane = (unsigned)lane_id(), below = (1u << lane) - 1u;
+    unsigned head = 0u, len = 0u;  // warp-uniform; head stays a multiple of four
+    for (int base = s; base < e; base += 64) {
+        const int j0 = base + (int)lane, j1 = j0 + 32;
+        bool keep0 = false, keep1 = false;
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (j0 < e) p0 = ldg4(a.posw + j0);
+        if (j1 < e) p1 = ldg4(a.posw + j1);
+        auto reach = [&](const float4 p) {
+            const float ex = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
+            const float ey = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
+            const float ez = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
+            return fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < g.cull_r2;
+        };
+        if (j0 < e) keep0 = reach(p0);
+        if (j1 < e) keep1 = reach(p1);
+        const unsigned m0 = __ballot_sync(0xffffffffu, keep0), m1 = __ballot_sync(0xffffffffu, keep1);
+        if (keep0) {
+            const unsigned at = (head + len + __popc(m0 & below)) & (kListLen - 1);
+            sts4(lst + (at << 4), p0);
+            sts4(lst_v + (at << 4), ldg4(a.veli + j0));
+        }
+        if (keep1) {
+            const unsigned at = (head + len + __popc(m0) + __popc(m1 & below)) & (kListLen - 1);
+            sts4(lst + (at << 4), p1);
+            sts4(lst_v + (at << 4), ldg4(a.veli + j1));
+        }
+        len += __popc(m0) + __popc(m1);
+        __syncwarp();
+        while (len >= 4u) {
+            const unsigned at = (head & (kListLen - 1)) << 4;
+            walk_group_mixed<LOWFIX>(h, run, tabrow_s, tabrow, boid_acc, a, g, im, lst + at, lst_v + at);
+            head += 4u;
+            len -= 4u;
+        }
+        __syncwarp();  // the lists are read before the next chunk appends to them
+    }
+    if (len > 0u) {
+        if (lane < 4u - len) {
+            // (type 0 and zero velocity: the parked particle is out of everybody's range)
+            const unsigned at = (head + len + lane) & (kListLen - 1);
+            sts4(lst + (at << 4), make_float4(kDummyPos, kDummyPos, kDummyPos, 0.0f));
+            sts4(lst_v + (at << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        __syncwarp();
+        const unsigned at = (head & (kListLen - 1)) << 4;
+        walk_group_mixed<LOWFIX>(h, run, tabrow_s, tabrow, boid_acc, a, g, im, lst + at, lst_v + at);
+        __syncwarp();
+    }
+    h.ax += ax0; h.ay += ay0; h.az += az0;
+}
+
+__device__ __forceinline__ void walk_image_mixed(Home& h, BoidRun& run, RowAddr tabrow_s,
+                                                 const PairParam* __restrict__ tabrow, float* __restrict__ boid_acc,
+                                                 const ForceArgs& a, const Geometry& g, const Box& b, int sx, int sy,
+                                                 int sz, int s, int e, unsigned lst, unsigned lst_v)
+{
+    const Image im = make_image(h, g, sx, sy, sz);
+    if (__any_sync(0xffffffffu, im.up))
+        walk_culled_mixed<true>(h, run, tabrow_s, tabrow, boid_acc, a, g, im, b, sx, sy, sz, s, e, lst, lst_v);
+    else
+        walk_culled_mixed<false>(h, run, tabrow_s, tabrow, boid_acc, a, g, im, b, sx, sy, sz, s, e, lst, lst_v);
+}
+
 // Choice of the LOWFIX variant for the lanes that are converged here (every lane of a code
 // path walks the same sequence of runs, possibly empty).  The variant does not change a
 // lane's result when its own `lo` parts are zero, so the vote only saves instructions.
@@ -1052,7 +1274,7 @@ __device__ __noinline__ float3 quirk_walk(float hx, float hy, float hz, int type
 #endif
 template <int KIND, int MODE, int SPLIT>
 #ifndef GOF_MIXED_MINBLOCKS
-#define GOF_MIXED_MINBLOCKS 6
+#define GOF_MIXED_MINBLOCKS 4
 #endif
 #ifndef GOF_BOIDS_MINBLOCKS
 #define GOF_BOIDS_MINBLOCKS 6
@@ -1074,7 +1296,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     const int T = a.T;
     char* tabAB = reinterpret_cast<char*>(tab + T * T);  // T rows of kRowBytes (see RowAddr)
     char* behind = tabAB + T * kRowBytes;
-    float* boid_acc = reinterpret_cast<float*>(behind) + threadIdx.x;
+    float* boid_acc = reinterpret_cast<float*>(behind) + threadIdx.x * 4;  // this thread's first float4 (boid_vec)
     float* part = reinterpret_cast<float*>(behind) + hl;  // SPLIT > 1 only
     // Clusters kind, behind `part`: every warp's list of surviving candidates (walk_culled) and,
     // behind all the lists, those of their slots (literal z-wrap walk only)
@@ -1082,21 +1304,33 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                           (SPLIT > 1 ? kSplitRuns * 3 * kSplitHomes * 4u : 0u);
     const unsigned lst = wmem + (threadIdx.x >> 5) * (kListLen * 16u);
     const unsigned lst_j = wmem + (blockDim.x >> 5) * (kListLen * 16u) + (threadIdx.x >> 5) * (kListLen * 4u);
+    // mixed kind: every warp's lists of surviving positions and velocities, behind the per-type sums
+    const unsigned mmem = (unsigned)__cvta_generic_to_shared(behind) + (unsigned)T * kBoidSlots * kForceThreads * 4u;
+    const unsigned mlst = mmem + (threadIdx.x >> 5) * (kListLen * 32u), mlst_v = mlst + kListLen * 16u;
     for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
         const PairParam pp = a.table[q];
         tab[q] = pp;
         const int r = q / T, c = q - r * T;
-        *reinterpret_cast<float4*>(tabAB + r * kRowBytes + c * 16) = pp.a;
-        *reinterpret_cast<float2*>(tabAB + r * kRowBytes + kRowB + c * 16) = make_float2(pp.b.x, pp.b.y);
+        float4 ea = pp.a, eb = make_float4(pp.b.x, pp.b.y, 0.0f, 0.0f);
+        if (KIND == kKindMixed && ((a.kind_rows[r] >> c) & 1u)) {  // Boids-kind pair: see pair_mixed
+            ea = make_float4(pp.a.x, 0.0f, -pp.a.y, 0.0f);
+            eb = make_float4(0.0f, 0.0f, 1.0f, 1.0f / (pp.a.x * pp.a.x));
+        }
+        *reinterpret_cast<float4*>(tabAB + r * kRowBytes + c * 16) = ea;
+        *reinterpret_cast<float4*>(tabAB + r * kRowBytes + kRowB + c * 16) = eb;
     }
     BoidQueue queue;
     queue.base = 0u;
     queue.count = 0;
     queue.fx = queue.fy = queue.fz = 0.0f;
     if (BOIDS) {
-        for (int q = 0; q < T * kBoidSlots; ++q) boid_acc[q * kForceThreads] = 0.0f;
+        for (int q = 0; q < T; ++q) {
+            *boid_vec(boid_acc, q, 0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *boid_vec(boid_acc, q, 1) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         // the queue sits behind the per-type sums; entry k of this lane at base + k * 512
-        queue.base = (unsigned)__cvta_generic_to_shared(boid_acc + T * kBoidSlots * kForceThreads);
+        queue.base = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float*>(behind) + T * kBoidSlots * kForceThreads +
+                                                        threadIdx.x);
     }
     __syncthreads();
 
@@ -1221,10 +1455,52 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     // nothing).
     bool as_warp = false;
 #ifndef GOF_NO_WARP_WALK
-    if (KIND == kKindClusters)  // (one row of cells: one layer, so `quirk` is the same for all lanes)
+    if (KIND == kKindClusters || KIND == kKindMixed)  // (one row of cells: one layer, so `quirk` is the same for all lanes)
         as_warp = __reduce_min_sync(0xffffffffu, (unsigned)cyz) == __reduce_max_sync(0xffffffffu, (unsigned)cyz);
+    if (KIND == kKindMixed && quirk) as_warp = false;  // the literal z-wrap layers of a mixed system walk per lane
 #endif
-    if (as_warp && quirk) {
+    if (KIND == kKindMixed && as_warp) {
+        // mixed kind: one walk for the warp, unified branch-free pairs (walk_culled_mixed)
+        const Box box = warp_box(h);
+        const int cx_min = (int)__reduce_min_sync(0xffffffffu, (unsigned)cx);
+        const int cx_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)cx);
+        BoidRun run;
+        run.c = run.rx = run.ry = run.rz = run.vx = run.vy = run.vz = 0.0f;
+        run.t = -1;
+        for (int dzi = dz_lo; dzi <= dz_hi; ++dzi) {
+            int nl = lz + dzi, sz = 0;
+            if (g.is3d) {
+                const int ngz = gz + dzi;
+                if (ngz < 0) { sz = 1; if (g.index_wrap_z) nl += g.nbz; }
+                else if (ngz >= g.nbz) { sz = -1; if (g.index_wrap_z) nl -= g.nbz; }
+            }
+            if (dzi == skip_dz) continue;  // across the z boundary, reference wrap: no interaction
+            for (int dyi = -1; dyi <= 1; ++dyi) {
+                int ny = cy + dyi, sy = 0;
+                if (ny < 0) { ny += g.nby; sy = 1; }
+                else if (ny >= g.nby) { ny -= g.nby; sy = -1; }
+                const int rb = (nl * g.nby + ny) * g.nbx;
+                const int lo = cx_min > 0 ? cx_min - 1 : 0;
+                const int hi = cx_max < g.nbx - 1 ? cx_max + 1 : g.nbx - 1;
+                walk_image_mixed(h, run, tabrow_s, tabrow, boid_acc, a, g, box, 0, sy, sz, a.pstart[rb + lo],
+                                 a.pstart[rb + hi] + a.count[rb + hi], mlst, mlst_v);
+                const float ax0 = h.ax, ay0 = h.ay, az0 = h.az;
+                h.ax = h.ay = h.az = 0.0f;
+                if (cx_min == 0) {
+                    const int s = a.pstart[rb + g.nbx - 1];
+                    walk_image_mixed(h, run, tabrow_s, tabrow, boid_acc, a, g, box, 1, sy, sz, s,
+                                     s + a.count[rb + g.nbx - 1], mlst, mlst_v);
+                }
+                if (cx_max == g.nbx - 1) {
+                    const int s = a.pstart[rb];
+                    walk_image_mixed(h, run, tabrow_s, tabrow, boid_acc, a, g, box, -1, sy, sz, s, s + a.count[rb], mlst,
+                                     mlst_v);
+                }
+                h.ax += ax0; h.ay += ay0; h.az += az0;
+            }
+        }
+        boidrun_store(run, boid_acc);  // the epilogue reads the slots
+    } else if (as_warp && quirk) {
         // bottom / top layer in GOF_WRAP_REFERENCE mode: the same walk by the literal rules, out of line
         const Box box = warp_box(h);
         const int cx_min = (int)__reduce_min_sync(0xffffffffu, (unsigned)cx);
@@ -1362,27 +1638,26 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     if (BOIDS) {
         const float spd = sqrtf(h.vx * h.vx + h.vy * h.vy + h.vz * h.vz);
         for (int t = 0; t < T; ++t) {
-            const float* slot = boid_acc + t * kBoidSlots * kForceThreads;
-            const float cnt = slot[0];
+            const float4 sc = *boid_vec(boid_acc, t, 0), sv = *boid_vec(boid_acc, t, 1);
+            const float cnt = sc.x;
             if (MODE == kModeScatter && a.boid_counts && valid) {
                 const size_t o = (size_t)t * a.n_total + id;
                 a.boid_counts[o] = (int)cnt;
-                a.boid_acc_x[o] = fmaf(cnt, h.x, slot[1 * kForceThreads]);
-                a.boid_acc_y[o] = fmaf(cnt, h.y, slot[2 * kForceThreads]);
-                a.boid_acc_z[o] = fmaf(cnt, h.z, slot[3 * kForceThreads]);
-                a.boid_vel_x[o] = slot[4 * kForceThreads];
-                a.boid_vel_y[o] = slot[5 * kForceThreads];
-                a.boid_vel_z[o] = slot[6 * kForceThreads];
+                a.boid_acc_x[o] = fmaf(cnt, h.x, sc.y);
+                a.boid_acc_y[o] = fmaf(cnt, h.y, sc.z);
+                a.boid_acc_z[o] = fmaf(cnt, h.z, sc.w);
+                a.boid_vel_x[o] = sv.x;
+                a.boid_vel_y[o] = sv.y;
+                a.boid_vel_z[o] = sv.z;
             }
             if (((h.kinds >> t) & 1u) && cnt > 0.0f) {
                 const PairParam q = tab[h.type * T + t];
                 const float ic = 1.0f / cnt;
-                const float mx = slot[4 * kForceThreads] * ic, my = slot[5 * kForceThreads] * ic,
-                            mz = slot[6 * kForceThreads] * ic;
+                const float mx = sv.x * ic, my = sv.y * ic, mz = sv.z * ic;
                 const float proj = spd > 10.0f ? (mx * h.vx + my * h.vy + mz * h.vz) / spd : 0.0f;
-                h.ax += q.a.w * (slot[1 * kForceThreads] * ic) + q.a.z * (mx - proj * h.vx);
-                h.ay += q.a.w * (slot[2 * kForceThreads] * ic) + q.a.z * (my - proj * h.vy);
-                h.az += q.a.w * (slot[3 * kForceThreads] * ic) + q.a.z * (mz - proj * h.vz);
+                h.ax += q.a.w * (sc.y * ic) + q.a.z * (mx - proj * h.vx);
+                h.ay += q.a.w * (sc.z * ic) + q.a.z * (my - proj * h.vy);
+                h.az += q.a.w * (sc.w * ic) + q.a.z * (mz - proj * h.vz);
             }
         }
     }
