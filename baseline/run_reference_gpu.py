@@ -34,6 +34,13 @@ SYSTEMS = {
     "hive_benchmark_2d_n2000": dict(clus=[1000, 1000], boid=[0], limits=(100, 100, 0)),
     "hive_default_3d_mixed_n14000": dict(clus=[2000] * 4, boid=[2000] * 3, limits=(100, 100, 100)),
 }
+# --large: BASELINE.json configs[1] (Clusters 3D, 5 species, N = 1M at the density of the 3D run above)
+# through the reference's own constructor and kernels.  NOTE: on B200 the reference's kernels FAULT at this
+# size (CUDA error 700, illegal address, in the first core_step: see profiles/r02_reference_numba.json), which
+# also poisons the CUDA context of the process; kept for the record, do not run it with anything else.
+LARGE = {
+    "baseline_config1_clusters3d_n1m": dict(clus=[200_000] * 5, boid=[0], limits=(414.913,) * 3, steps=10),
+}
 
 
 def clocks():
@@ -80,7 +87,8 @@ def time_reference(steps: int) -> dict:
             sim.update()  # hive.py's dummy call: compiles every kernel
             cuda.synchronize()
             compile_s = time.perf_counter() - t0
-            for _ in range(10):
+            steps = cfg.get("steps", steps)
+            for _ in range(min(10, steps)):
                 sim.core_step()
             cuda.synchronize()
             t0 = time.perf_counter()
@@ -109,6 +117,7 @@ def time_engine(steps: int) -> dict:
         np.random.seed(12345)
         sim = Simulation(np.array(cfg["clus"]), np.array(cfg["boid"]), limits=cfg["limits"], seed=434, device="cuda:0")
         sim.update()
+        steps = max(cfg.get("steps", steps), 50) if "steps" in cfg else steps
         for _ in range(10):
             sim.core_step()
         torch.cuda.synchronize()
@@ -127,7 +136,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "reference_numba.json"))
+    ap.add_argument("--large", action="store_true", help="also BASELINE.json configs[1] at N = 1M")
     args = ap.parse_args()
+    if args.large:
+        SYSTEMS.update(LARGE)
     res = {"clocks_before": clocks()}
     res["reference_numba_cuda"] = time_reference(args.steps)
     res["clocks_between"] = clocks()
