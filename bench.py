@@ -141,8 +141,9 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu_index = gpu_index
+    def __init__(self, gpu_indices):
+        """gpu_indices: the GPUs of this job (rank 0 samples all of them with one nvidia-smi)."""
+        self.gpu_indices = list(gpu_indices)
         self.rows = []
         self.proc = None
         self.thread = None
@@ -150,7 +151,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
+                ["nvidia-smi", "--id=" + ",".join(str(i) for i in self.gpu_indices), f"--query-gpu={self.QUERY}",
                  "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
@@ -187,8 +188,9 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_min_mhz": float(min(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "gpus": len(self.gpu_indices), "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -538,10 +540,15 @@ def main():
 
     def timed_run(n, steps, warmup, e2e_steps, evolve):
         hs, eng, runner, step, e2e_step = make_job(n)
+        # clocks of every GPU of the job, sampled by rank 0 from the warm-up on (nvidia-smi needs a
+        # moment to start; the timed region of a short run is over before its first sample)
+        sampler = ClockSampler(range(world)) if rank == 0 else None
+        if sampler:
+            sampler.start()
         step(warmup)
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        if sampler:
+            sampler.rows.clear()  # (what follows is the timed region and, if it is short, more of the same load)
         eng.timing(True)
         lib.gof_reset_launch_count()
         # Every timed step starts with a cold L2: a 256 MiB buffer (2x the 126 MB L2) is overwritten
@@ -566,7 +573,19 @@ def main():
         launches = int(lib.gof_launch_count())
         force_ms, force_launches = eng.force_time()
         eng.timing(False)
-        clocks = sampler.stop()
+        # a timed region of a few tens of milliseconds ends before nvidia-smi's next sample: keep the
+        # same load on (untimed) until there are at least three samples per GPU, at most ~1.5 s
+        t_load = time.perf_counter()
+        while True:
+            enough = torch.tensor([1 if (sampler is None or len(sampler.rows) >= 3 * world or
+                                         time.perf_counter() - t_load > 1.5) else 0], device=device)
+            if world > 1:
+                dist.broadcast(enough, 0)
+            if int(enough.item()):
+                break
+            step(10)
+            torch.cuda.synchronize(device)
+        clocks = sampler.stop() if sampler else None
         stats = eng.pair_stats() if hasattr(eng, "pair_stats") else None
         out = {"hs": hs, "ms_total": ms_total, "launches": launches, "force_ms": force_ms,
                "force_launches": force_launches, "clocks": clocks, "stats": stats,

@@ -554,13 +554,21 @@ class SlabRunner:
         return out
 
 
+class P2PUnavailable(RuntimeError):
+    """The peer-memory transport cannot be set up on this job (raised on EVERY rank alike)."""
+
+
 class P2PRunner:
     """The slabs of a job exchange through peer memory (gof_slab_connect / gof_slab_step_p2p).
 
     `slabs`: {global slab index: SlabEngine} of this process.  With torch.distributed initialised
     (one slab per rank is the normal case) the arenas are shared with CUDA IPC: every rank exports
     a handle, all-gathers handles and window descriptions once, and maps its peers.  Without it all
-    slabs must be local (tests on one GPU).  A step is ONE C call; nothing is read back."""
+    slabs must be local (tests on one GPU).  A step is ONE C call; nothing is read back.
+
+    Set-up failures (no IPC between the ranks' devices, a driver that refuses the mapping) are
+    agreed on collectively after every stage, so that all ranks raise P2PUnavailable together and a
+    caller can fall back to the send/recv transport (make_runner does)."""
 
     transport = "p2p (peer-memory stores over NVLink, flag waits on the stream, no host sync)"
 
@@ -572,52 +580,82 @@ class P2PRunner:
         self._opened = []
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized() if group_ready is None else group_ready
+        self._distributed = distributed
         first = next(iter(self.slabs.values()))
         self.index = first.index
         if any(e.index != self.index for e in self.slabs.values()):
             raise ValueError("P2PRunner: the local slabs must share one device")
         W = self.world_slabs
-        infos = {}
-        for s, e in self.slabs.items():
-            w = (C.c_int64 * 12)()
-            _lib.check(self.lib.gof_slab_window(e._handle, w, 12))
-            infos[s] = list(w)
-        bases = {s: e._arena_ptr for s, e in self.slabs.items()}
-        if len(self.slabs) < W:
+        if len(self.slabs) < W and not distributed:
+            raise ValueError("P2PRunner: slabs missing and torch.distributed is not initialised")
+
+        def agree(error):
+            """All ranks learn whether ANY of them failed the stage; everybody raises then."""
             if not distributed:
-                raise ValueError("P2PRunner: slabs missing and torch.distributed is not initialised")
-            mine = {}
+                if error is not None:
+                    raise P2PUnavailable(str(error))
+                return
+            flag = torch.tensor([0 if error is None else 1], dtype=torch.int32, device=first.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag.item()):
+                self._unmap()
+                raise P2PUnavailable(str(error) if error is not None else "another rank could not set it up")
+
+        # ---- stage 1: describe and export the local arenas
+        infos, bases, mine, err = {}, {}, {}, None
+        try:
             for s, e in self.slabs.items():
-                h = (C.c_ubyte * 64)()
-                off = C.c_int64()
-                _lib.check(self.lib.gof_ipc_export(e._arena_ptr, h, C.byref(off)))
-                mine[s] = (bytes(h), int(off.value), infos[s], torch.cuda.current_device())
+                w = (C.c_int64 * 12)()
+                _lib.check(self.lib.gof_slab_window(e._handle, w, 12))
+                infos[s] = list(w)
+                bases[s] = e._arena_ptr
+                if len(self.slabs) < W:
+                    h = (C.c_ubyte * 64)()
+                    off = C.c_int64()
+                    with torch.cuda.device(self.index):
+                        _lib.check(self.lib.gof_ipc_export(e._arena_ptr, h, C.byref(off)))
+                    mine[s] = (bytes(h), int(off.value), infos[s])
+        except Exception as exc:  # noqa: BLE001
+            err = exc
+        agree(err)
+        # ---- stage 2: map the peers
+        err = None
+        if len(self.slabs) < W:
             gathered = [None] * dist.get_world_size()
             dist.all_gather_object(gathered, mine)
-            for part in gathered:
-                for s, (h, off, info, _dev) in part.items():
-                    infos[s] = info
-                    if s in self.slabs:
-                        continue
-                    base = C.c_void_p()
-                    buf = (C.c_ubyte * 64).from_buffer_copy(h)
-                    with torch.cuda.device(self.index):
-                        _lib.check(self.lib.gof_ipc_open(buf, C.byref(base)))
-                    self._opened.append(base.value)
-                    bases[s] = base.value + off
-        if sorted(bases) != list(range(W)):
-            raise ValueError(f"P2PRunner: need every slab 0..{W - 1}, have {sorted(bases)}")
-        base_arr = (C.c_void_p * W)(*[bases[s] for s in range(W)])
-        info_arr = (C.c_int64 * (12 * W))(*[x for s in range(W) for x in infos[s]])
-        with torch.cuda.device(self.index):
-            for s, e in self.slabs.items():
-                _lib.check(self.lib.gof_slab_connect(e._handle, s, W, base_arr, info_arr))
-            torch.cuda.synchronize(self.index)
+            try:
+                for part in gathered:
+                    for s, (h, off, info) in part.items():
+                        infos[s] = info
+                        if s in self.slabs:
+                            continue
+                        base = C.c_void_p()
+                        buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                        with torch.cuda.device(self.index):
+                            _lib.check(self.lib.gof_ipc_open(buf, C.byref(base)))
+                        self._opened.append(base.value)
+                        bases[s] = base.value + off
+                if sorted(bases) != list(range(W)):
+                    raise ValueError(f"need every slab 0..{W - 1}, have {sorted(bases)}")
+            except Exception as exc:  # noqa: BLE001
+                err = exc
+            agree(err)
+        # ---- stage 3: connect (zeroes this slab's flag block), then nobody stores before everybody is through
+        err = None
+        try:
+            base_arr = (C.c_void_p * W)(*[bases[s] for s in range(W)])
+            info_arr = (C.c_int64 * (12 * W))(*[x for s in range(W) for x in infos[s]])
+            with torch.cuda.device(self.index):
+                for s, e in self.slabs.items():
+                    _lib.check(self.lib.gof_slab_connect(e._handle, s, W, base_arr, info_arr))
+                torch.cuda.synchronize(self.index)
+        except Exception as exc:  # noqa: BLE001
+            err = exc
+        agree(err)
         if distributed:
-            dist.barrier()  # every slab's flag block is zeroed before anybody stores into it
+            dist.barrier()
         self._handles = (C.c_void_p * len(self.slabs))(*[self.slabs[s]._handle for s in sorted(self.slabs)])
         self._side = torch.cuda.Stream(device=self.index, priority=-1)
-        self._distributed = distributed
 
     def step(self, n_steps: int = 1, timestep=None):
         first = next(iter(self.slabs.values()))
@@ -630,6 +668,11 @@ class P2PRunner:
     def gather_state(self, num_particles: int):
         return SlabRunner.gather_state(self, num_particles)
 
+    def _unmap(self):
+        for b in self._opened:
+            self.lib.gof_ipc_close(b)
+        self._opened = []
+
     def close(self):
         """Unmap the peers (every rank must have finished stepping: barrier first)."""
         if self._opened:
@@ -637,9 +680,7 @@ class P2PRunner:
             if self._distributed:
                 import torch.distributed as dist
                 dist.barrier()
-            for b in self._opened:
-                self.lib.gof_ipc_close(b)
-            self._opened = []
+            self._unmap()
 
     def __del__(self):
         try:
@@ -649,13 +690,21 @@ class P2PRunner:
 
 
 def make_runner(eng, world: int, device=None, transport: str = "auto"):
-    """The runner of a one-slab-per-rank job (torch.distributed initialised): peer-memory
-    transport unless `transport == "nccl"` (or GOF_SLAB_TRANSPORT=nccl)."""
+    """The runner of a one-slab-per-rank job (torch.distributed initialised): the peer-memory
+    transport; `transport == "nccl"` (or GOF_SLAB_TRANSPORT=nccl) selects NCCL send/recv, and
+    "auto" falls back to it when peer memory cannot be set up (all ranks decide together)."""
     import torch.distributed as dist
     choice = os.environ.get("GOF_SLAB_TRANSPORT", transport)
     rank = dist.get_rank()
     if choice in ("auto", "p2p"):
-        return P2PRunner({rank: eng}, world)
+        try:
+            return P2PRunner({rank: eng}, world)
+        except P2PUnavailable as exc:
+            if choice == "p2p":
+                raise
+            if rank == 0:
+                import warnings
+                warnings.warn(f"peer-memory transport unavailable ({exc}): using NCCL send/recv", RuntimeWarning)
     runner = SlabRunner({rank: eng}, world, DistComm(world, device=device))
     runner.transport = "nccl (send/recv of halo layers and migration records, sizes all-gathered per step)"
     return runner
