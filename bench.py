@@ -420,7 +420,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-north-star", action="store_true",
-                    help="at 8 GPUs, skip the second timed configuration (3D Clusters N=16M)")
+                    help="skip the extra timed configurations of the default run (BASELINE.json configs[2..4], "
+                         "and at 8 GPUs the north_star configuration, 3D Clusters N=16M)")
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false",
                     help="do not overwrite a 256 MiB buffer between timed steps")
     ap.add_argument("--wrap", default="reference", choices=["reference", "minimage"],
@@ -472,8 +473,9 @@ def main():
     pin = lambda a, dt=np.float32: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory()
     parity = None
 
-    def make_job(n):
-        """Engine, step(k) and e2e_step() for `n` particles per GPU."""
+    def make_job(n, want_e2e=True):
+        """Engine, step(k) and e2e_step() for `n` particles per GPU (pinned host buffers only when
+        the end-to-end leg will run)."""
         hs = global_state(args, world, n)
         if world == 1:
             # ---- one GPU: the resident engine on the whole periodic box ---------------------
@@ -483,7 +485,8 @@ def main():
             h_acc = [pin(init[k]) for k in ("acc_x", "acc_y", "acc_z")]
             h_types = pin(hs["particle_type_index_array"], np.int32)
             bufs = {"in": (h_pos, h_vel, h_acc),
-                    "out": tuple([torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)] for _ in range(3))}
+                    "out": tuple([torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
+                                 for _ in range(3)) if want_e2e else None}
             eng = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]), device=device,
                                  wrap_mode=wrap_mode)
             eng.upload(h_pos, h_types, vel=h_vel, acc=h_acc)
@@ -513,17 +516,18 @@ def main():
         step = lambda k: runner.step(k, args.timestep)
         # end to end: pinned, preallocated host buffers of `capacity` entries, ping-pong like the
         # one-GPU path; the particle count of a slab changes from step to step (migration)
-        mk = lambda dt=torch.float32: torch.empty(cap, dtype=dt).pin_memory()
-        host = [dict(pos=[mk() for _ in range(3)], vel=[mk() for _ in range(3)], acc=[mk() for _ in range(3)],
-                     types=mk(torch.int32), ids=mk(torch.int32), n=0) for _ in range(2)]
-        for k in range(3):
-            host[0]["pos"][k][:n] = torch.from_numpy(pos[k])
-            host[0]["vel"][k][:n] = 0
-            host[0]["acc"][k][:n] = 0
-        host[0]["types"][:n] = torch.from_numpy(types)
-        host[0]["ids"][:n] = torch.from_numpy(ids)
-        host[0]["n"] = n
-        cur = [0]
+        host, cur = [], [0]
+        if want_e2e:
+            mk = lambda dt=torch.float32: torch.empty(cap, dtype=dt).pin_memory()
+            host = [dict(pos=[mk() for _ in range(3)], vel=[mk() for _ in range(3)], acc=[mk() for _ in range(3)],
+                         types=mk(torch.int32), ids=mk(torch.int32), n=0) for _ in range(2)]
+            for k in range(3):
+                host[0]["pos"][k][:n] = torch.from_numpy(pos[k])
+                host[0]["vel"][k][:n] = 0
+                host[0]["acc"][k][:n] = 0
+            host[0]["types"][:n] = torch.from_numpy(types)
+            host[0]["ids"][:n] = torch.from_numpy(ids)
+            host[0]["n"] = n
 
         def e2e_step():
             a, b = host[cur[0]], host[cur[0] ^ 1]
@@ -539,7 +543,7 @@ def main():
                                    lambda e: make_runner(e, world, device, transport=args.transport))
 
     def timed_run(n, steps, warmup, e2e_steps, evolve):
-        hs, eng, runner, step, e2e_step = make_job(n)
+        hs, eng, runner, step, e2e_step = make_job(n, want_e2e=e2e_steps > 0)
         # clocks of every GPU of the job, sampled by rank 0 from the warm-up on (nvidia-smi needs a
         # moment to start; the timed region of a short run is over before its first sample)
         sampler = ClockSampler(range(world)) if rank == 0 else None
@@ -627,12 +631,37 @@ def main():
     n = args.particles
     res = timed_run(n, args.steps, args.warmup, args.e2e_steps, args.evolve if world == 1 else 0)
     north = None
-    if world == 8 and args.workload == "clusters3d" and n != 2_000_000 and not args.no_north_star:
+    others = {}
+    default_run = args.workload == "clusters3d" and n == 1_000_000 and not args.no_north_star
+
+    def extra(workload, n_per_gpu, steps, what):
+        """Another BASELINE.json configuration as a short second timed run of the same job."""
+        keep = args.workload
+        args.workload = workload
+        try:
+            r = timed_run(n_per_gpu, steps, 3, 0, 0)
+        finally:
+            args.workload = keep
+        rec = {"workload": what, "value": r["value"], "unit": "particle-updates/s", "ms_per_step": r["ms_per_step"],
+               "force_ms_per_step": r["force_ms"] / steps, "steps": steps, "warmup": 3, "n_gpus": world,
+               "particles_per_gpu": n_per_gpu, "clocks": r["clocks"]}
+        if r["stats"]:
+            rec["pairs_in_range_per_particle"] = r["stats"]["in_range"] / max(r["stats"]["n"], 1)
+        return rec
+
+    if default_run and world == 8:
         # BASELINE.json's target configuration, as a second timed run of the same job
-        r2 = timed_run(2_000_000, args.steps, args.warmup, 0, 0)
-        north = {"workload": "Clusters 3D, 5 species, N=16000000 on 8 GPUs (2M per GPU)", "value": r2["value"],
-                 "unit": "particle-updates/s", "ms_per_step": r2["ms_per_step"], "steps": args.steps,
-                 "target": 1.0e10, "clocks": r2["clocks"]}
+        north = extra("clusters3d", 2_000_000, args.steps, "Clusters 3D, 5 species, N=16000000 on 8 GPUs (2M per GPU)")
+        north["target"] = 1.0e10
+        others["configs3_mixed3d_16m"] = extra("mixed3d", 2_000_000, 20,
+                                               "BASELINE configs[3]: mixed Clusters+Boids 3D, 8 species, N=16M over 8 GPUs")
+    if default_run and world == 1:
+        others["configs2_boids3d_4m"] = extra("boids3d", 4_000_000, 30, "BASELINE configs[2]: Boids 3D, 3 species, N=4M, one GPU")
+        others["mixed3d_2m"] = extra("mixed3d", 2_000_000, 20,
+                                     "mixed Clusters+Boids 3D, 8 species, N=2M, one GPU (configs[3]'s per-GPU share)")
+    if default_run:
+        others["configs4_clusters3d_16m_per_gpu"] = extra(
+            "clusters3d", 16_000_000, 10, f"BASELINE configs[4]: Clusters 3D weak scaling, 16M per GPU, N={16 * world}M")
 
     if rank == 0:
         hs = res["hs"]
@@ -697,6 +726,8 @@ def main():
             line["parity_check"] = parity
         if north is not None:
             line["north_star_16m"] = north
+        if others:
+            line["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, args.seed, args.density, args.cpu_seconds)
         print(json.dumps(line), flush=True)
