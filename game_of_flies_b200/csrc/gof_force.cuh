@@ -208,6 +208,13 @@ __device__ __forceinline__ void shifted(float v, int s, float L, float L_lo, flo
 __device__ __forceinline__ Image make_image(const Home& h, const Geometry& g, int sx, int sy, int sz)
 {
     Image im;
+    if ((sx | sy | sz) == 0) {  // no periodic image (most runs): the two-sums below would yield exactly this
+        im.x = h.x; im.y = h.y; im.z = h.z;
+        im.lx = im.ly = im.lz = 0.0f;
+        im.shifts = pack_shifts(0, 0, 0);
+        im.up = false;
+        return im;
+    }
     shifted(h.x, sx, g.Lx, g.Lx_lo, im.x, im.lx);
     shifted(h.y, sy, g.Ly, g.Ly_lo, im.y, im.ly);
     shifted(h.z, sz, g.Lz, g.Lz_lo, im.z, im.lz);
@@ -1600,10 +1607,12 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
                 // the cell across the periodic x boundary (an empty run for interior home cells:
                 // every lane makes the same calls, so the warp votes inside stay convergent)
                 const bool xedge = cx == 0 || cx == g.nbx - 1;
-                const int wc = cx == 0 ? g.nbx - 1 : 0;
-                s = a.pstart[rb + wc];
-                e = (valid && xedge) ? s + a.count[rb + wc] : s;
-                run_image<KIND>(h, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e, queue);
+                if (__any_sync(__activemask(), valid && xedge)) {  // (an empty run leaves h as it is: skip it)
+                    const int wc = cx == 0 ? g.nbx - 1 : 0;
+                    s = a.pstart[rb + wc];
+                    e = (valid && xedge) ? s + a.count[rb + wc] : s;
+                    run_image<KIND>(h, tabrow_s, tabrow, boid_acc, a, g, cx == 0 ? 1 : -1, sy, sz, s, e, queue);
+                }
                 if (SPLIT > 1) {
                     store_partial(part, 2 * row + 1, h);
                     h.ax = h.ay = h.az = 0.0f;
