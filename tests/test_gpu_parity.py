@@ -551,3 +551,39 @@ def test_full_size_properties_boids3d_4m(gof):
         assert np.all(np.isfinite(out[k]))
     assert np.all(out["pos"] >= 0) and np.all(out["pos"] <= st["limits"][:, None])
     e.close()
+
+
+@pytest.mark.parametrize("kinds,T", [("clusters", 16), ("mixed", 16), ("boids", 16), ("mixed", 1), ("clusters", 1)])
+def test_species_count_limits(gof, kinds, T):
+    """GOF_MAX_TYPES = 16 species (the largest shared-memory footprint of every kernel kind) and a
+    single species: one step and the acceleration field against the oracle."""
+    if kinds == "mixed" and T == 1:
+        pytest.skip("a mixed system needs two species")
+    st = random_state([max(6000 // T, 40)] * T, (90, 100, 110), seed=13, kinds=kinds, speed=4.0)
+    check_engine_step(gof, st, None)
+    check_accelerator(gof, st, orc.WRAP_REFERENCE)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 129])
+@pytest.mark.parametrize("kinds", ["clusters", "mixed", "boids"])
+def test_tiny_and_ragged_particle_counts(gof, kinds, n):
+    """Fewer particles than a warp / a block, and counts that leave ragged last warps."""
+    T = 2
+    counts = [n - n // 2, n // 2] if n > 1 else [1, 0]
+    st = random_state(counts, (45, 50, 55), seed=n, kinds=kinds, speed=3.0)
+    check_engine_step(gof, st, None)
+    check_engine_step(gof, st, 0.02, wrap_mode=orc.WRAP_MINIMAGE)
+
+
+@pytest.mark.parametrize("kinds", ["clusters", "mixed"])
+def test_everything_in_a_few_cells(gof, kinds):
+    """A clump: 6000 particles inside two neighbouring cells of a large, otherwise empty box (runs
+    of thousands of candidates through the survivor lists, empty cells everywhere else)."""
+    st = random_state([1500] * 4, (200, 200, 200), seed=21, kinds=kinds, speed=2.0)
+    r = st["r_max"]
+    rng = np.random.default_rng(5)
+    pos = np.stack([rng.random(st["n"]) * 1.9 * r + 3 * r, rng.random(st["n"]) * 0.9 * r + 3 * r,
+                    rng.random(st["n"]) * 0.9 * r + 3 * r])
+    st["pos"] = f32_state(pos)
+    check_engine_step(gof, st, None)
+    check_accelerator(gof, st, orc.WRAP_MINIMAGE)

@@ -142,3 +142,18 @@ def test_engine_entry_points_reject_slab_engines():
     # the caller's current device is left alone by every entry point
     assert torch.cuda.current_device() == e.index
     e.close()
+
+
+@pytest.mark.parametrize("transport", ["p2p", "copies"])
+def test_a_slab_that_starts_empty(transport):
+    """All particles start in the lower half of the box: the upper slabs begin EMPTY, receive their
+    first particles through migration, and boundary layers / halos of zero particles travel."""
+    st = random_state([5000] * 3, (100, 100, 260), seed=9, kinds="clusters", speed=12.0)
+    st["pos"][2] *= 0.45
+    st["pos"] = st["pos"].astype(np.float32).astype(np.float64)
+    steps = 12
+    want = run_single(st, steps, None, orc.WRAP_MINIMAGE)
+    got, moved = run_slabs(st, 4, steps, None, orc.WRAP_MINIMAGE, transport=transport)
+    assert (got["owner"] >= 0).all()
+    for k in ("pos", "vel", "acc"):
+        assert np.array_equal(got[k], want[k]), f"{transport}: {k} differs from the single-engine result"
