@@ -170,9 +170,10 @@ class SlabEngine:
         return n
 
     def pair_stats(self) -> dict:
+        n = self.count()  # (also refreshes the library's host-side count from the device words)
         out = (C.c_ulonglong * 3)()
         _lib.check(self.lib.gof_engine_pair_stats(self._handle, self.wrap_mode, out, self._stream()))
-        return {"n": max(self.count(), 1), "candidates": int(out[0]),
+        return {"n": max(n, 1), "candidates": int(out[0]),
                 "evaluated": int(out[1]), "in_range": int(out[2])}
 
     def set_parameters(self, parameter_matrix):
