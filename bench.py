@@ -576,6 +576,7 @@ def main():
         ms_total = timed_steps(steps)
         launches = int(lib.gof_launch_count())
         force_ms, force_launches = eng.force_time()
+        phases = eng.phase_times() if hasattr(eng, "phase_times") else None
         eng.timing(False)
         # a timed region of a few tens of milliseconds ends before nvidia-smi's next sample: keep the
         # same load on (untimed) until there are at least three samples per GPU, at most ~1.5 s
@@ -591,7 +592,7 @@ def main():
             torch.cuda.synchronize(device)
         clocks = sampler.stop() if sampler else None
         stats = eng.pair_stats() if hasattr(eng, "pair_stats") else None
-        out = {"hs": hs, "ms_total": ms_total, "launches": launches, "force_ms": force_ms,
+        out = {"hs": hs, "ms_total": ms_total, "launches": launches, "force_ms": force_ms, "phases": phases,
                "force_launches": force_launches, "clocks": clocks, "stats": stats,
                "value": world * n * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps}
         # ---- end to end through the public API with host buffers --------------------------
@@ -720,6 +721,8 @@ def main():
             "gpu_launches": res["launches"],
             "roofline": roofline,
         }
+        if res.get("phases") and res["phases"]["steps"]:
+            line["slab_phases_ms_per_step"] = res["phases"]  # (rank 0's slab; peer-memory transport)
         if "steady" in res:
             line["steady_state"] = res["steady"]
         if parity is not None:

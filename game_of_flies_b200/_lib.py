@@ -80,6 +80,7 @@ SIGNATURES = {
     "gof_slab_connect": (_i, [_vp, _i, _i, _vp, _vp]),
     "gof_slab_step_p2p": (_i, [_vp, _i, _i, C.c_float, _i, _vp, _vp]),
     "gof_slab_check": (_i, [_vp, _vp, _vp]),
+    "gof_slab_phase_times": (_i, [_vp, _vp, _vp]),
     "gof_ipc_export": (_i, [_vp, _vp, _vp]),
     "gof_ipc_open": (_i, [_vp, _vp]),
     "gof_ipc_close": (_i, [_vp]),

@@ -48,10 +48,9 @@ k_hash_count(const float4* __restrict__ posw, const float4* __restrict__ veli,
              const float* __restrict__ py, const float* __restrict__ pz, int n,
              const int* __restrict__ n_limit, const __grid_constant__ Geometry g,
              int* __restrict__ cell_of, int* __restrict__ off, int* __restrict__ count,
-             MigrateOut mig, const int* __restrict__ base_word = nullptr)
+             MigrateOut mig)
 {
-    // base_word (slab mode, peer-memory transport): the first slot to look at lives on the device
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + (base_word ? *base_word : 0);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_limit) n = min(n, *n_limit);  // slab mode: the real count lives on the device
     int cell = -1;
     if (i < n) {
@@ -223,9 +222,19 @@ __global__ void __launch_bounds__(kBinThreads)
 k_scatter_ids(const float4* __restrict__ veli, int n, const int* __restrict__ n_limit,
               const int* __restrict__ cell_of, const int* __restrict__ off,
               const int* __restrict__ start, int* __restrict__ slot_id,
-              const float4* __restrict__ posw, unsigned* __restrict__ slot_key)
+              const float4* __restrict__ posw, unsigned* __restrict__ slot_key,
+              int* __restrict__ slab_words = nullptr, const int* __restrict__ slab_error = nullptr,
+              int num_cells = 0, int per_layer = 0, int top = 0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slab_words && i == 0) {
+        // slab mode, peer-memory transport: the scan is done, so the sizes of this step are known:
+        // {live particles, population of the bottom owned layer, of the top owned layer, error flag}
+        slab_words[0] = start[num_cells];
+        slab_words[1] = start[2 * per_layer] - start[per_layer];
+        slab_words[2] = start[(top + 1) * per_layer] - start[top * per_layer];
+        slab_words[3] = *slab_error;
+    }
     if (n_limit) n = min(n, *n_limit);
     if (i >= n) return;
     const int dst = start[cell_of[i]] + off[i];
@@ -343,20 +352,10 @@ namespace gof {
 __global__ void __launch_bounds__(kBinThreads)
 k_append_arrivals(const float4* __restrict__ from_down, const float4* __restrict__ from_up, int capacity,
                   int base, float4* __restrict__ posw, float4* __restrict__ veli,
-                  float4* __restrict__ acc, int* __restrict__ words,
-                  const int* __restrict__ base_word = nullptr, int slot_capacity = 0, int* error = nullptr)
+                  float4* __restrict__ acc, int* __restrict__ words)
 {
-    int n_down = min(__float_as_int(from_down[0].x), capacity);
-    int n_up = min(__float_as_int(from_up[0].x), capacity);
-    if (base_word) {
-        // peer-memory transport: the number of resident slots lives on the device, and so does the
-        // check that the arrivals fit (the host learns of a failure from the sticky error flag)
-        base = *base_word;
-        if (base + n_down + n_up > slot_capacity) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(error, 5);
-            n_down = n_up = 0;
-        }
-    }
+    const int n_down = min(__float_as_int(from_down[0].x), capacity);
+    const int n_up = min(__float_as_int(from_up[0].x), capacity);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) {
         words[0] = n_down + n_up;

@@ -1314,6 +1314,24 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     // mixed kind: every warp's lists of surviving positions and velocities, behind the per-type sums
     const unsigned mmem = (unsigned)__cvta_generic_to_shared(behind) + (unsigned)T * kBoidSlots * kForceThreads * 4u;
     const unsigned mlst = mmem + (threadIdx.x >> 5) * (kListLen * 32u), mlst_v = mlst + kListLen * 16u;
+    // The home range.  Slab launches whose ranges live on the device are sized for an upper bound:
+    // a surplus block leaves here, before it has touched shared memory or a barrier.
+    int home_begin = a.home_begin, home_count = a.home_count;
+    int home_begin2 = a.home_begin2, home_count2 = a.home_count2;
+    if (a.interior_words) {  // owned particles that are in neither boundary layer
+        const int live = a.interior_words[0], lo = a.interior_words[1], hi = a.interior_words[2];
+        home_begin = lo;
+        home_count = live - lo - hi;
+        if ((int)blockIdx.x * kHomes >= home_count) return;  // (block-uniform; also: no interior layer)
+    }
+    if (a.boundary_words) {  // the bottom and the top owned layer
+        const int live = a.boundary_words[0], lo = a.boundary_words[1], hi = a.boundary_words[2];
+        home_begin = 0;
+        home_count = lo;
+        home_begin2 = live - hi;
+        home_count2 = hi;
+        if ((int)blockIdx.x * kHomes >= lo + hi) return;
+    }
     for (int q = threadIdx.x; q < T * T; q += blockDim.x) {
         const PairParam pp = a.table[q];
         tab[q] = pp;
@@ -1341,22 +1359,6 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     }
     __syncthreads();
 
-    int home_begin = a.home_begin, home_count = a.home_count;
-    int home_begin2 = a.home_begin2, home_count2 = a.home_count2;
-    if (a.interior_words) {  // owned particles that are in neither boundary layer
-        const int live = a.interior_words[0], lo = a.interior_words[1], hi = a.interior_words[2];
-        home_begin = lo;
-        home_count = live - lo - hi;
-        if (home_count <= 0) return;  // (block-uniform: one or two owned layers)
-    }
-    if (a.boundary_words) {  // the bottom and the top owned layer
-        const int live = a.boundary_words[0], lo = a.boundary_words[1], hi = a.boundary_words[2];
-        home_begin = 0;
-        home_count = lo;
-        home_begin2 = live - hi;
-        home_count2 = hi;
-        if (lo + hi <= 0) return;
-    }
     // Block -> particles mapping, rotated so that the blocks of the TOP z layer run first, then the
     // bottom layer, then the rest: in GOF_WRAP_REFERENCE mode those two layers take the literal path
     // (~3x the work per particle) and would otherwise sit at the very end of the grid, stretching

@@ -5,12 +5,12 @@
 // Per step a slab
 //   1. packs the particles that left its layers (k_hash_count) and pushes the two record
 //      buffers into the neighbours' receive buffers                         (k_push_migration)
-//   2. waits for the two buffers addressed to it                            (k_wait_tags)
+//   2. waits for the two buffers addressed to it, appends and bins them      (k_arrivals_p2p)
 //   3. sorts; pushes its bottom / top layer -- contiguous slices of the sorted arrays -- and
 //      their per-cell counts into the neighbours' halo regions              (k_push_halo)
 //   4. waits for its two halo layers, then runs the boundary layers' forces (k_wait_tags)
 //   5. publishes its maximum squared speed to EVERY slab                    (k_publish_speed)
-// and the next step's timestep kernel waits for all of them                 (k_prepare_dt_p2p).
+// and the next step's arrivals kernel waits for all of them                 (k_arrivals_p2p).
 //
 // A flag is one 64-bit word {step tag << 32 | payload} written with a single store after a
 // system-scope fence: a reader that sees the tag sees the data.  Buffers are single (the speed
@@ -165,32 +165,82 @@ __global__ void k_publish_speed(const StepScalars* __restrict__ s, int parity,
     if (t < world) store_flag(slots[t], make_flag(tag, s->max_sq_speed_bits[parity]));
 }
 
-// k_prepare_dt of a slab: the adaptive timestep needs the maximum over ALL slabs, i.e. every
-// slab's published word for this step (`speed_in` = this slab's slot array of `parity`).
-__global__ void k_prepare_dt_p2p(StepScalars* s, int parity, float fixed_dt,
-                                 const unsigned long long* __restrict__ speed_in, int world, unsigned tag,
-                                 int* error)
+// Phase 2's front end in ONE launch: every block waits for the two record buffers addressed to this
+// slab, block 0 also settles the timestep (it waits for every slab's published maximum speed: the
+// one global dependency of a step), then thread k appends arrival k behind the resident
+// particles and bins it.  Also clears the headers of this
+// slab's send buffers for the next step: their push is behind us on the stream.
+//   words: [0] arrivals, [1] slots in use, [2] sticky error, [4] live particles before this step
+__global__ void __launch_bounds__(kBinThreads)
+k_arrivals_p2p(const unsigned long long* __restrict__ f_below, const unsigned long long* __restrict__ f_above,
+               unsigned tag, const float4* __restrict__ from_down, const float4* __restrict__ from_up,
+               int mig_capacity, float4* __restrict__ posw, float4* __restrict__ veli, float4* __restrict__ acc,
+               int* __restrict__ words, int slot_capacity, const __grid_constant__ Geometry g,
+               int* __restrict__ cell_of, int* __restrict__ off, int* __restrict__ count, StepScalars* s,
+               int parity, float fixed_dt, const unsigned long long* __restrict__ speed_in, int world,
+               float4* __restrict__ send_down, float4* __restrict__ send_up)
 {
-    unsigned bits = 0u;
-    bool ok = true;
-    if (fixed_dt < 0.0f && (int)threadIdx.x < world) {
+    if (threadIdx.x < 2) {
         unsigned long long v = 0;
-        ok = wait_flag(speed_in + threadIdx.x, tag, &v);
-        bits = (unsigned)(v & 0xffffffffu);
+        if (!wait_flag(threadIdx.x ? f_above : f_below, tag, &v)) atomicExch(words + 2, kErrPeerTimeout);
     }
-    bits = __reduce_max_sync(0xffffffffu, bits);
-    ok = __all_sync(0xffffffffu, ok);
-    if (threadIdx.x == 0) {
-        float dt = fixed_dt;
-        if (fixed_dt < 0.0f) {
-            if (!ok) atomicExch(error, kErrPeerTimeout);
-            const double m = sqrt((double)__uint_as_float(bits));
-            dt = (m > 1e-6) ? (float)(0.4 / m) : 0.1f;
-            s->max_sq_speed_bits[parity] = bits;  // (what a single engine's word would hold)
+    if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) {
+        // the timestep of this step: the maximum over every slab's published word
+        const int ln = (int)threadIdx.x - 32;
+        unsigned bits = 0u;
+        bool ok = true;
+        if (fixed_dt < 0.0f && ln < world) {
+            unsigned long long v = 0;
+            ok = wait_flag(speed_in + ln, tag, &v);
+            bits = (unsigned)(v & 0xffffffffu);
         }
-        s->dt = dt;
-        s->max_sq_speed_bits[parity ^ 1] = 0u;
+        bits = __reduce_max_sync(0xffffffffu, bits);
+        ok = __all_sync(0xffffffffu, ok);
+        if (ln == 0) {
+            float dt = fixed_dt;
+            if (fixed_dt < 0.0f) {
+                if (!ok) atomicExch(words + 2, kErrPeerTimeout);
+                const double m = sqrt((double)__uint_as_float(bits));
+                dt = (m > 1e-6) ? (float)(0.4 / m) : 0.1f;
+                s->max_sq_speed_bits[parity] = bits;
+            }
+            s->dt = dt;
+            s->max_sq_speed_bits[parity ^ 1] = 0u;
+        }
     }
+    __syncthreads();  // the flags have been seen: the buffers are complete
+    const int base = words[4];
+    int n_down = min(__float_as_int(from_down[0].x), mig_capacity);
+    int n_up = min(__float_as_int(from_up[0].x), mig_capacity);
+    if (base + n_down + n_up > slot_capacity) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(words + 2, 5);
+        n_down = n_up = 0;
+    }
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) {
+        words[0] = n_down + n_up;
+        words[1] = base + n_down + n_up;
+        send_down[0] = make_float4(0.f, 0.f, 0.f, 0.f);  // (record counters of the next step's leavers)
+        send_up[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (k >= n_down + n_up) return;
+    const float4* rec = k < n_down ? from_down + 1 + 3 * (size_t)k : from_up + 1 + 3 * (size_t)(k - n_down);
+    const float4 p = rec[0];
+    posw[base + k] = p;
+    veli[base + k] = rec[1];
+    acc[base + k] = rec[2];
+    // its cell in the local grid; an arrival that is not in an owned layer cannot happen
+    const int cx = bin_coord(p.x, g.bsx, g.nbx), cy = bin_coord(p.y, g.bsy, g.nby);
+    int lz = bin_coord(p.z, g.bsz, g.nbz) - g.layer_base;
+    if (lz >= g.nbz) lz -= g.nbz;
+    if (lz < 0) lz += g.nbz;
+    int cell = cx + g.nbx * (cy + g.nby * lz);
+    if (lz <= 0 || lz >= g.nlz - 1) {
+        atomicExch(words + 2, 1);
+        cell = g.num_cells;
+    }
+    cell_of[base + k] = cell;
+    off[base + k] = atomicAdd(&count[cell], 1);
 }
 
 // Halo cell table with the halo regions at FIXED slots (capacity, capacity + halo_capacity), so

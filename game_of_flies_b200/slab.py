@@ -169,6 +169,16 @@ class SlabEngine:
         torch.cuda.current_stream(self.index).synchronize()
         return n
 
+    def phase_times(self):
+        """Per-step phase times of the peer-memory transport since timing(True), in ms: prefix (hash,
+        migration, sort), interior forces, halo + boundary forces (side stream), whole step."""
+        out = (C.c_float * 4)()
+        k = C.c_int()
+        _lib.check(self.lib.gof_slab_phase_times(self._handle, out, C.byref(k)))
+        steps = max(int(k.value), 1)
+        return {"prefix": out[0] / steps, "interior_forces": out[1] / steps, "halo_and_boundary_forces": out[2] / steps,
+                "step": out[3] / steps, "steps": int(k.value)}
+
     def pair_stats(self) -> dict:
         n = self.count()  # (also refreshes the library's host-side count from the device words)
         out = (C.c_ulonglong * 3)()

@@ -298,6 +298,10 @@ int gof_slab_connect(gof_engine *e, int rank, int world, void *const *bases, con
 int gof_slab_step_p2p(gof_engine *const *slabs, int n_slabs, int n_steps, float timestep, int wrap_mode,
                       void *main_stream, void *side_stream);
 int gof_slab_check(gof_engine *e, int *n_live, void *stream);
+/* Phase times of the peer-memory steps since gof_engine_timing(e, 1) (first slab of each call), summed
+ * over *steps steps, in ms: {start -> sorted, sorted -> interior forces done, sorted -> boundary forces
+ * done (side stream), start -> end}.  Synchronises on the recorded events. */
+int gof_slab_phase_times(gof_engine *e, float *out4, int *steps);
 
 /* CUDA IPC plumbing for gof_slab_connect between processes: the 64-byte handle of the device
  * allocation that holds d_ptr and d_ptr's offset inside it; open / close a peer's handle. */
