@@ -332,7 +332,7 @@ static size_t force_smem_bytes(int T, int kind, int split)
            (kind == kKindBoids ? (size_t)kQueueDepth * kForceThreads * sizeof(unsigned) : 0) +
            (kind == kKindMixed ? (size_t)(kForceThreads / 32) * kListLen * 2 * sizeof(float4) : 0) +
            (split > 1 ? (size_t)kSplitRuns * 3 * kSplitHomes * sizeof(float) : 0) +
-           (kind == kKindClusters ? (size_t)(split > 1 ? split : kForceThreads / 32) * kListLen * (sizeof(float4) + sizeof(int)) : 0);
+           (kind == kKindClusters ? (size_t)(split > 1 ? split : kForceThreads / 32) * kWalkCap * (sizeof(float4) + sizeof(int)) : 0);
 }
 
 // cudaFuncSetAttribute is per device: remember per kernel instantiation which devices have it

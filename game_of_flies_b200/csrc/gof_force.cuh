@@ -257,6 +257,22 @@ __device__ __forceinline__ float dist2_tiny(float dx, float dy, float dz)
     return fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, kTinyD2)));
 }
 
+// profile(dist) / dist of a Clusters-kind pair, formed without dist itself: inside r_min
+// f_min / d - k0, beyond it f_max / d - s1 |1 - mid / d| (the same piecewise-linear profile as the
+// reference's, acceleration_updater.py:369-383, divided through by d; one multiply-add less per pair
+// than profile(d2 * inv) * inv and no less accurate: the rounding of rsqrt enters one term instead
+// of two).  `qa` = {r_min^2, k0, f_min, mid}, `qb` = {s1, f_max}, inv = 1 / d.  EVERY Clusters-kind
+// path evaluates a pair with this function (hot loops, literal z-wrap, cold repairs), so that what
+// a repair takes back is bit for bit what the hot loop added.
+__device__ __forceinline__ float clusters_scale(const float4 qa, const float2 qb, float d2, float inv)
+{
+    const float s_in = fmaf(qa.z, inv, -qa.y);
+    const float u = fmaf(-qa.w, inv, 1.0f);
+    const float v = qb.y * inv;
+    const float s_tri = fmaf(-qb.x, fabsf(u), v);
+    return d2 < qa.x ? s_in : s_tri;
+}
+
 // Cold path of the Clusters loop: a pair inside the guard band of r_max^2, or closer
 // than the reference's 1e-10 lower bound.  The hot loop added the pair's force iff its
 // fp32 d2 was below r2_lo; here the reference's float64 decision is taken and the
@@ -273,13 +289,10 @@ __device__ __noinline__ float3 repair_pair_clusters(const Geometry& g, float xi,
     const double e = exact_dist2(g, xi, yi, zi, xj, yj, zj, shifts);
     const bool wanted = (1e-10 < e) && (e < g.r2d);
     if (added == wanted) return make_float3(0.f, 0.f, 0.f);
-    const float4 qa = q->a;
+    float4 qa = q->a;
     const float4 qb = q->b;
-    const float inv = fast_rsqrt(d2);
-    const float dist = d2 * inv;
-    const float f_in = fmaf(-qa.y, dist, qa.z);
-    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-    float s = (dist < qa.x ? f_in : f_tri) * inv;
+    qa.x = qa.x * qa.x;  // r_min^2, as k_force's prologue stores it for the hot loop
+    float s = clusters_scale(qa, make_float2(qb.x, qb.y), d2, fast_rsqrt(d2));
     if (added) s = -s;  // take it back
     return make_float3(-s * dx, -s * dy, -s * dz);
 }
@@ -287,8 +300,9 @@ __device__ __noinline__ float3 repair_pair_clusters(const Geometry& g, float xi,
 // Branch-free Clusters pair.  With ~830 candidates and ~130 neighbours per particle at least one
 // lane of a warp accepts almost every candidate, so a branch around the force evaluation never
 // skips it; it only adds divergence bookkeeping and serialises the loop.  The evaluation is
-// therefore done for every candidate and masked: adds the force iff d2 < r2_lo and returns d2 so
-// that the caller can spot the rare pairs that need the cold path.
+// therefore done for every candidate and its three multiply-adds predicated on d2 < r2_lo
+// (the self pair adds s * 0 = 0 with s finite); returns d2 so that the caller can spot the rare
+// pairs that need the cold path.
 template <bool LOWFIX>
 __device__ __forceinline__ float pair_clusters(Home& h, RowAddr tabrow_s, const Geometry& g,
                                                const Image& im, const float4 pj)
@@ -299,15 +313,12 @@ __device__ __forceinline__ float pair_clusters(Home& h, RowAddr tabrow_s, const 
     const unsigned at = tabrow_s.a + ((unsigned)__float_as_int(pj.w) << 4);
     const float4 qa = lds4(at);
     const float2 qb = lds2(at + kRowB);
-    const float inv = fast_rsqrt(d2);
-    const float dist = d2 * inv;
-    const float f_in = fmaf(-qa.y, dist, qa.z);
-    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-    float s = (dist < qa.x ? f_in : f_tri) * inv;
-    s = d2 < g.r2_lo ? s : 0.0f;
-    h.ax = fmaf(-s, dx, h.ax);  // the self pair contributes s * 0 = 0 with s finite
-    h.ay = fmaf(-s, dy, h.ay);
-    h.az = fmaf(-s, dz, h.az);
+    const float s = clusters_scale(qa, qb, d2, fast_rsqrt(d2));
+    if (d2 < g.r2_lo) {
+        h.ax = fmaf(-s, dx, h.ax);
+        h.ay = fmaf(-s, dy, h.ay);
+        h.az = fmaf(-s, dz, h.az);
+    }
     return d2;
 }
 
@@ -518,6 +529,12 @@ __device__ __forceinline__ float pair_clusters_quirk(Home& h, RowAddr tabrow_s, 
 __device__ __forceinline__ void repair_quirk(float3& rep, const Home& h, const PairParam* __restrict__ tabrow,
                                              const Geometry& g, const Image& im, int sx, int sy, bool direct,
                                              const float4 pj);
+__device__ __forceinline__ void quirk_dz(const Geometry& g, bool direct, float zi, float yi, float zj,
+                                         float yj, float& dz, float& relz);
+__device__ __noinline__ float3 repair_quirk_clusters(const Geometry& g, bool direct, float hx, float hy,
+                                                     float hz, float pjx, float pjy, float pjz, int sx,
+                                                     int sy, float dx, float dy, float dz, float d2,
+                                                     const PairParam* q);
 
 // ---- Clusters kind: one walk for the whole warp, culled against the box of its home particles --
 // When the 32 home particles of a warp sit in one row of cells (same y and z cell), the union of
@@ -556,7 +573,11 @@ __device__ __forceinline__ Box warp_box(const Home& h)
     return b;
 }
 
-constexpr int kListLen = 128;  // survivors a warp can hold (a power of two): fewer than 4 left over + 64 of a chunk
+constexpr int kListLen = 128;  // mixed kind: survivors a warp can hold (a ring, a power of two)
+// Clusters kind: the survivor list is linear.  A run appends chunk after chunk behind the < 4
+// entries that still wait for a full group; only when the next chunk of 64 might not fit are
+// those moved to the front (runs of more than ~3 chunks: crowded cells).
+constexpr int kWalkCap = 192;
 
 __device__ __forceinline__ void sts4(unsigned saddr, const float4 v)
 {
@@ -573,57 +594,84 @@ __device__ __forceinline__ float4 lds4v(unsigned saddr)
     return v;
 }
 
-// four survivors from the warp's list (one broadcast 16-byte shared-memory load each).
+// Four survivors from the warp's list (one broadcast 16-byte shared-memory load each), every lane,
+// no branch.  A group in which this lane has a pair for the cold path (guard band of r_max^2, or
+// closer than the reference's 1e-10 bound -- the lane's own particle is one, once per stencil) is
+// only NOTED: mark = mark * 4096 + address.  After the chunk, mark == 0 says nothing to do, a
+// value below 2^18 (the shared-memory window) is the address of the one noted group, anything
+// larger means several (addresses grow along the loop and are >= 64, so this holds whatever
+// overflows).  A branch to the cold code per group, taken once in ~100 groups, cost 2-3 % of the
+// loop's instructions and kept the compiler from scheduling across it.
 // LITERAL: the home cells are in the bottom / top layer in GOF_WRAP_REFERENCE mode; the pair is
 // evaluated by the literal z-wrap rules, in the role (`direct` or not, see quirk_home) that follows
 // from the survivor's slot `at_j` against the threshold `own` of the lane.
 template <bool LITERAL, bool LOWFIX>
-__device__ __forceinline__ void walk_group(Home& h, float3& rep, RowAddr tabrow_s,
-                                           const PairParam* __restrict__ tabrow, const Geometry& g,
-                                           const Image& im, unsigned at, unsigned at_j, int own, int sx, int sy)
+__device__ __forceinline__ void walk_group(Home& h, unsigned& mark, RowAddr tabrow_s, const Geometry& g,
+                                           const Image& im, unsigned at, unsigned at_j, int own)
 {
     const float4 p0 = lds4v(at), p1 = lds4v(at + 16u), p2 = lds4v(at + 32u), p3 = lds4v(at + 48u);
     float d0, d1, d2, d3;
-    bool r0 = true, r1 = true, r2 = true, r3 = true;
     if (LITERAL) {
         const float4 jj = lds4v(at_j);
-        r0 = __float_as_int(jj.x) >= own; r1 = __float_as_int(jj.y) >= own;
-        r2 = __float_as_int(jj.z) >= own; r3 = __float_as_int(jj.w) >= own;
-        d0 = pair_clusters_quirk(h, tabrow_s, g, im, r0, p0);
-        d1 = pair_clusters_quirk(h, tabrow_s, g, im, r1, p1);
-        d2 = pair_clusters_quirk(h, tabrow_s, g, im, r2, p2);
-        d3 = pair_clusters_quirk(h, tabrow_s, g, im, r3, p3);
+        d0 = pair_clusters_quirk(h, tabrow_s, g, im, __float_as_int(jj.x) >= own, p0);
+        d1 = pair_clusters_quirk(h, tabrow_s, g, im, __float_as_int(jj.y) >= own, p1);
+        d2 = pair_clusters_quirk(h, tabrow_s, g, im, __float_as_int(jj.z) >= own, p2);
+        d3 = pair_clusters_quirk(h, tabrow_s, g, im, __float_as_int(jj.w) >= own, p3);
     } else {
         d0 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p0);
         d1 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p1);
         d2 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p2);
         d3 = pair_clusters<LOWFIX>(h, tabrow_s, g, im, p3);
     }
-    const bool b0 = !(d0 < g.r2_lo) && d0 < g.r2_hi, b1 = !(d1 < g.r2_lo) && d1 < g.r2_hi,
-               b2 = !(d2 < g.r2_lo) && d2 < g.r2_hi, b3 = !(d3 < g.r2_lo) && d3 < g.r2_hi;
-    const bool tiny = fminf(fminf(d0, d1), fminf(d2, d3)) <= 1e-10f;
-    if (b0 | b1 | b2 | b3 | tiny) {
-        if (LITERAL) {
-            if (needs_repair(g, d0)) repair_quirk(rep, h, tabrow, g, im, sx, sy, r0, p0);
-            if (needs_repair(g, d1)) repair_quirk(rep, h, tabrow, g, im, sx, sy, r1, p1);
-            if (needs_repair(g, d2)) repair_quirk(rep, h, tabrow, g, im, sx, sy, r2, p2);
-            if (needs_repair(g, d3)) repair_quirk(rep, h, tabrow, g, im, sx, sy, r3, p3);
-        } else {
-            if (needs_repair(g, d0)) repair(rep, h, tabrow, g, im, p0);
-            if (needs_repair(g, d1)) repair(rep, h, tabrow, g, im, p1);
-            if (needs_repair(g, d2)) repair(rep, h, tabrow, g, im, p2);
-            if (needs_repair(g, d3)) repair(rep, h, tabrow, g, im, p3);
-        }
-    }
+    const unsigned noted = mark * 4096u + at;
+    const bool ok = (d0 < g.r2_lo || !(d0 < g.r2_hi)) && (d1 < g.r2_lo || !(d1 < g.r2_hi)) &&
+                    (d2 < g.r2_lo || !(d2 < g.r2_hi)) && (d3 < g.r2_lo || !(d3 < g.r2_hi)) &&
+                    fminf(fminf(d0, d1), fminf(d2, d3)) > 1e-10f;
+    mark = ok ? mark : noted;
 }
 
-// `lst`: shared-memory address of the warp's survivor list (kListLen float4, a ring).  Per chunk
-// of 64 candidates every lane loads two and tests them against the box; the survivors are appended
-// in order (ballot + prefix count), and the list is consumed four at a time, left-overs carried
-// to the next chunk.  The run's last group is padded with a particle parked far outside the box.
+// The cold path of a chunk: entries [at, end) of the list once more, in order, for the lanes that
+// flagged one of them.  The squared distance is formed exactly as the hot loop formed it (the `lo`
+// parts of an image that was not shifted upwards are zero: adding them changes nothing).
+template <bool LITERAL>
+__device__ __noinline__ float3 repair_entries(float3 rep, float hx, float hy, float hz, float imx, float imy,
+                                              float imz, float lx, float ly, float lz, int shifts,
+                                              const PairParam* __restrict__ tabrow, const Geometry& g,
+                                              unsigned at, unsigned end, unsigned at_j, int own, int sx, int sy)
+{
+    for (; at != end; at += 16u, at_j += 4u) {
+        const float4 pj = lds4v(at);
+        const PairParam* q = tabrow + __float_as_int(pj.w);
+        float3 f;
+        if (LITERAL) {
+            int j;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(j) : "r"(at_j) : "memory");
+            const bool direct = j >= own;
+            float dz, relz;
+            quirk_dz(g, direct, hz, hy, pj.z, pj.y, dz, relz);
+            const float dx = (imx - pj.x) + lx, dy = (imy - pj.y) + ly;
+            const float d2 = dist2_tiny(dx, dy, dz);
+            if (!needs_repair(g, d2)) continue;
+            f = repair_quirk_clusters(g, direct, hx, hy, hz, pj.x, pj.y, pj.z, sx, sy, dx, dy, dz, d2, q);
+        } else {
+            const float dx = (imx - pj.x) + lx, dy = (imy - pj.y) + ly, dz = (imz - pj.z) + lz;
+            if (!needs_repair(g, dist2_tiny(dx, dy, dz))) continue;
+            f = repair_pair_clusters(g, hx, hy, hz, imx, imy, imz, lx, ly, lz, shifts, pj.x, pj.y, pj.z, q);
+        }
+        rep.x += f.x; rep.y += f.y; rep.z += f.z;
+    }
+    return rep;
+}
+
+// `lst`: shared-memory address of the warp's survivor list (kWalkCap float4).  Per chunk of 64
+// candidates every lane loads two and tests them against the box; the survivors are appended in
+// order (ballot + prefix count) and the list is consumed four at a time with a running address,
+// the < 4 left-overs waiting where they are for the next chunk.  The run's last group is padded
+// with a particle parked far outside the box.
 //
 // LITERAL: `im` carries no z shift; the z separation of a pair is whatever the literal rules make
 // it, so a candidate survives if it is in reach of the box as it is or one box length up or down.
+// `lst_j`: the survivors' slots (LITERAL only).
 template <bool LITERAL, bool LOWFIX>
 __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const PairParam* __restrict__ tabrow,
                                             const ForceArgs& a, const Geometry& g, const Image& im,
@@ -640,7 +688,7 @@ __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const Pai
     const float loy = b.loy + ty - g.cull_slack, hiy = b.hiy + ty + g.cull_slack;
     const float loz = b.loz + tz - g.cull_slack, hiz = b.hiz + tz + g.cull_slack;
     const unsigned lane = (unsigned)lane_id(), below = (1u << lane) - 1u;
-    unsigned head = 0u, len = 0u;  // warp-uniform; head stays a multiple of four
+    unsigned head = 0u, tail = 0u;  // entries [head, tail) wait; warp-uniform; head is a multiple of four
     // chunks of 64 candidates, two per lane: half as many ballot / append / syncwarp rounds
     for (int base = s; base < e; base += 64) {
         const int j0 = base + (int)lane, j1 = j0 + 32;
@@ -661,38 +709,70 @@ __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const Pai
         };
         if (j0 < e) keep0 = reach(p0);
         if (j1 < e) keep1 = reach(p1);
+        if (tail + 64u > (unsigned)kWalkCap) {  // (warp-uniform, rare) make room: the waiting entries go to the front
+            float4 w = p0;
+            int wj = 0;
+            const bool mine = lane < tail - head;
+            if (mine) {
+                w = lds4v(lst + ((head + lane) << 4));
+                if (LITERAL) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wj) : "r"(lst_j + ((head + lane) << 2)) : "memory");
+            }
+            __syncwarp();
+            if (mine) {
+                sts4(lst + (lane << 4), w);
+                if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (lane << 2)), "r"(wj) : "memory");
+            }
+            tail -= head;
+            head = 0u;
+        }
         const unsigned m0 = __ballot_sync(0xffffffffu, keep0), m1 = __ballot_sync(0xffffffffu, keep1);
         if (keep0) {
-            const unsigned at = (head + len + __popc(m0 & below)) & (kListLen - 1);
+            const unsigned at = tail + __popc(m0 & below);
             sts4(lst + (at << 4), p0);
             if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (at << 2)), "r"(j0) : "memory");
         }
         if (keep1) {
-            const unsigned at = (head + len + __popc(m0) + __popc(m1 & below)) & (kListLen - 1);
+            const unsigned at = tail + __popc(m0) + __popc(m1 & below);
             sts4(lst + (at << 4), p1);
             if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (at << 2)), "r"(j1) : "memory");
         }
-        len += __popc(m0) + __popc(m1);
+        tail += __popc(m0) + __popc(m1);
         __syncwarp();
-        while (len >= 4u) {
-            const unsigned at = head & (kListLen - 1);
-            walk_group<LITERAL, LOWFIX>(h, rep, tabrow_s, tabrow, g, im, lst + (at << 4), lst_j + (at << 2), own, sx, sy);
-            head += 4u;
-            len -= 4u;
+        const unsigned stop = tail & ~3u;
+        if (stop != head) {
+            const unsigned first = lst + (head << 4), end = lst + (stop << 4);
+            unsigned mark = 0u, at = first, at_j = lst_j + (head << 2);
+            do {
+                walk_group<LITERAL, LOWFIX>(h, mark, tabrow_s, g, im, at, at_j, own);
+                at += 64u;
+                at_j += 16u;
+            } while (at != end);
+            if (__any_sync(0xffffffffu, mark != 0u)) {
+                if (mark != 0u) {  // one noted group: that one; several: the whole chunk once more
+                    const unsigned f = mark < (1u << 18) ? mark : first, t = mark < (1u << 18) ? mark + 64u : end;
+                    rep = repair_entries<LITERAL>(rep, h.x, h.y, h.z, im.x, im.y, im.z, im.lx, im.ly, im.lz, im.shifts,
+                                                  tabrow, g, f, t, lst_j + ((f - lst) >> 2), own, sx, sy);
+                }
+                __syncwarp();
+            }
+            head = stop;
         }
-        __syncwarp();  // the list is read before the next chunk appends to it
     }
-    if (len > 0u) {
-        if (lane < 4u - len) {
-            const unsigned at = (head + len + lane) & (kListLen - 1);
+    if (tail != head) {
+        if (lane < 4u - (tail - head)) {
+            const unsigned at = tail + lane;
             sts4(lst + (at << 4), make_float4(kDummyPos, kDummyPos, kDummyPos, 0.0f));
             if (LITERAL) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lst_j + (at << 2)), "r"(0) : "memory");
         }
         __syncwarp();
-        const unsigned at = head & (kListLen - 1);
-        walk_group<LITERAL, LOWFIX>(h, rep, tabrow_s, tabrow, g, im, lst + (at << 4), lst_j + (at << 2), own, sx, sy);
-        __syncwarp();
+        const unsigned first = lst + (head << 4);
+        unsigned mark = 0u;
+        walk_group<LITERAL, LOWFIX>(h, mark, tabrow_s, g, im, first, lst_j + (head << 2), own);
+        if (mark != 0u)
+            rep = repair_entries<LITERAL>(rep, h.x, h.y, h.z, im.x, im.y, im.z, im.lx, im.ly, im.lz, im.shifts, tabrow, g,
+                                          first, first + 64u, lst_j + (head << 2), own, sx, sy);
     }
+    __syncwarp();  // the list is read before the next run appends to it
     h.ax += rep.x; h.ay += rep.y; h.az += rep.z;
     h.ax += ax0; h.ay += ay0; h.az += az0;
 }
@@ -1003,13 +1083,10 @@ __device__ __noinline__ float3 repair_quirk_clusters(const Geometry& g, bool dir
     const double e = quirk_exact_d2(g, direct, hx, hy, hz, pjx, pjy, pjz, sx, sy);
     const bool wanted = (1e-10 < e) && (e < g.r2d);
     if (added == wanted) return make_float3(0.f, 0.f, 0.f);
-    const float4 qa = q->a;
+    float4 qa = q->a;
     const float4 qb = q->b;
-    const float inv = fast_rsqrt(d2);
-    const float dist = d2 * inv;
-    const float f_in = fmaf(-qa.y, dist, qa.z);
-    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-    float s = (dist < qa.x ? f_in : f_tri) * inv;
+    qa.x = qa.x * qa.x;
+    float s = clusters_scale(qa, make_float2(qb.x, qb.y), d2, fast_rsqrt(d2));
     if (added) s = -s;
     return make_float3(-s * dx, -s * dy, -s * dz);
 }
@@ -1026,15 +1103,12 @@ __device__ __forceinline__ float pair_clusters_quirk(Home& h, RowAddr tabrow_s, 
     const unsigned at = tabrow_s.a + ((unsigned)__float_as_int(pj.w) << 4);
     const float4 qa = lds4(at);
     const float2 qb = lds2(at + kRowB);
-    const float inv = fast_rsqrt(d2);
-    const float dist = d2 * inv;
-    const float f_in = fmaf(-qa.y, dist, qa.z);
-    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-    float s = (dist < qa.x ? f_in : f_tri) * inv;
-    s = d2 < g.r2_lo ? s : 0.0f;
-    h.ax = fmaf(-s, dx, h.ax);
-    h.ay = fmaf(-s, dy, h.ay);
-    h.az = fmaf(-s, dz, h.az);
+    const float s = clusters_scale(qa, qb, d2, fast_rsqrt(d2));
+    if (d2 < g.r2_lo) {
+        h.ax = fmaf(-s, dx, h.ax);
+        h.ay = fmaf(-s, dy, h.ay);
+        h.az = fmaf(-s, dz, h.az);
+    }
     return d2;
 }
 
@@ -1309,8 +1383,8 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     // behind all the lists, those of their slots (literal z-wrap walk only)
     const unsigned wmem = (unsigned)__cvta_generic_to_shared(behind) +
                           (SPLIT > 1 ? kSplitRuns * 3 * kSplitHomes * 4u : 0u);
-    const unsigned lst = wmem + (threadIdx.x >> 5) * (kListLen * 16u);
-    const unsigned lst_j = wmem + (blockDim.x >> 5) * (kListLen * 16u) + (threadIdx.x >> 5) * (kListLen * 4u);
+    const unsigned lst = wmem + (threadIdx.x >> 5) * (kWalkCap * 16u);
+    const unsigned lst_j = wmem + (blockDim.x >> 5) * (kWalkCap * 16u) + (threadIdx.x >> 5) * (kWalkCap * 4u);
     // mixed kind: every warp's lists of surviving positions and velocities, behind the per-type sums
     const unsigned mmem = (unsigned)__cvta_generic_to_shared(behind) + (unsigned)T * kBoidSlots * kForceThreads * 4u;
     const unsigned mlst = mmem + (threadIdx.x >> 5) * (kListLen * 32u), mlst_v = mlst + kListLen * 16u;
@@ -1337,6 +1411,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
         tab[q] = pp;
         const int r = q / T, c = q - r * T;
         float4 ea = pp.a, eb = make_float4(pp.b.x, pp.b.y, 0.0f, 0.0f);
+        if (KIND == kKindClusters) ea.x = pp.a.x * pp.a.x;  // clusters_scale compares squared distances
         if (KIND == kKindMixed && ((a.kind_rows[r] >> c) & 1u)) {  // Boids-kind pair: see pair_mixed
             ea = make_float4(pp.a.x, 0.0f, -pp.a.y, 0.0f);
             eb = make_float4(0.0f, 0.0f, 1.0f, 1.0f / (pp.a.x * pp.a.x));
