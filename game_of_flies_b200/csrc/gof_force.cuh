@@ -691,11 +691,10 @@ __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const Pai
     unsigned head = 0u, tail = 0u;  // entries [head, tail) wait; warp-uniform; head is a multiple of four
     // chunks of 64 candidates, two per lane: half as many ballot / append / syncwarp rounds
     for (int base = s; base < e; base += 64) {
+        // (no branch around the loads and the tests: a slot past the run's end re-reads its last
+        // candidate and is dropped by the comparison of its index)
         const int j0 = base + (int)lane, j1 = j0 + 32;
-        bool keep0 = false, keep1 = false;
-        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-        if (j0 < e) p0 = ldg4(a.posw + j0);
-        if (j1 < e) p1 = ldg4(a.posw + j1);
+        const float4 p0 = ldg4(a.posw + min(j0, e - 1)), p1 = ldg4(a.posw + min(j1, e - 1));
         auto reach = [&](const float4 p) {
             const float ex = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
             const float ey = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
@@ -707,8 +706,7 @@ __device__ __forceinline__ void walk_culled(Home& h, RowAddr tabrow_s, const Pai
             }
             return fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < g.cull_r2;
         };
-        if (j0 < e) keep0 = reach(p0);
-        if (j1 < e) keep1 = reach(p1);
+        const bool keep0 = reach(p0) && j0 < e, keep1 = reach(p1) && j1 < e;
         if (tail + 64u > (unsigned)kWalkCap) {  // (warp-uniform, rare) make room: the waiting entries go to the front
             float4 w = p0;
             int wj = 0;
