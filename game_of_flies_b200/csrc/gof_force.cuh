@@ -129,6 +129,22 @@ __device__ __forceinline__ float fast_rsqrt(float v)
     return r;
 }
 
+// profile(dist) / dist of a Clusters-kind pair, formed without dist itself: inside r_min
+// f_min / d - k0, beyond it f_max / d - s1 |1 - mid / d| (the same piecewise-linear profile as the
+// reference's, acceleration_updater.py:369-383, divided through by d; one multiply-add less per pair
+// than profile(d2 * inv) * inv and no less accurate: the rounding of rsqrt enters one term instead
+// of two).  `qa` = {r_min^2, k0, f_min, mid}, `qb` = {s1, f_max}, inv = 1 / d.  EVERY Clusters-kind
+// path evaluates a pair with this function (hot loops, literal z-wrap, cold repairs), so that what
+// a repair takes back is bit for bit what the hot loop added.
+__device__ __forceinline__ float clusters_scale(const float4 qa, const float2 qb, float d2, float inv)
+{
+    const float s_in = fmaf(qa.z, inv, -qa.y);
+    const float u = fmaf(-qa.w, inv, 1.0f);
+    const float v = qb.y * inv;
+    const float s_tri = fmaf(-qb.x, fabsf(u), v);
+    return d2 < qa.x ? s_in : s_tri;
+}
+
 // One accepted pair: add what j does to the home particle.
 //   (dx, dy, dz) = home - neighbour (after the periodic shift), d2 = |d|^2
 //   (rx, ry, rz) = neighbour - home as the reference accumulates it for cohesion
@@ -172,11 +188,10 @@ __device__ __forceinline__ void interact(Home& h, const PairParam* __restrict__ 
     const float dist = d2 * inv;
     const float4 qa = tabrow[tj].a;
     if (!BOIDS || !((h.kinds >> tj) & 1u)) {
-        // clusters(): piecewise linear profile, force along the separation vector
+        // clusters(): piecewise linear profile, force along the separation vector (the same
+        // arithmetic as the unified pair of the whole-warp walk, pair_mixed)
         const float4 qb = tabrow[tj].b;
-        const float f_in = fmaf(-qa.y, dist, qa.z);
-        const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-        const float s = (dist < qa.x ? f_in : f_tri) * inv;
+        const float s = clusters_scale(make_float4(qa.x * qa.x, qa.y, qa.z, qa.w), make_float2(qb.x, qb.y), d2, inv);
         h.ax = fmaf(-s, dx, h.ax);
         h.ay = fmaf(-s, dy, h.ay);
         h.az = fmaf(-s, dz, h.az);
@@ -255,22 +270,6 @@ constexpr float kTinyD2 = 1e-30f;  // keeps rsqrt finite for the self pair (whos
 __device__ __forceinline__ float dist2_tiny(float dx, float dy, float dz)
 {
     return fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, kTinyD2)));
-}
-
-// profile(dist) / dist of a Clusters-kind pair, formed without dist itself: inside r_min
-// f_min / d - k0, beyond it f_max / d - s1 |1 - mid / d| (the same piecewise-linear profile as the
-// reference's, acceleration_updater.py:369-383, divided through by d; one multiply-add less per pair
-// than profile(d2 * inv) * inv and no less accurate: the rounding of rsqrt enters one term instead
-// of two).  `qa` = {r_min^2, k0, f_min, mid}, `qb` = {s1, f_max}, inv = 1 / d.  EVERY Clusters-kind
-// path evaluates a pair with this function (hot loops, literal z-wrap, cold repairs), so that what
-// a repair takes back is bit for bit what the hot loop added.
-__device__ __forceinline__ float clusters_scale(const float4 qa, const float2 qb, float d2, float inv)
-{
-    const float s_in = fmaf(qa.z, inv, -qa.y);
-    const float u = fmaf(-qa.w, inv, 1.0f);
-    const float v = qb.y * inv;
-    const float s_tri = fmaf(-qb.x, fabsf(u), v);
-    return d2 < qa.x ? s_in : s_tri;
 }
 
 // Cold path of the Clusters loop: a pair inside the guard band of r_max^2, or closer
@@ -825,14 +824,15 @@ __device__ __forceinline__ void boidrun_load(BoidRun& r, const float* __restrict
 
 // One survivor, every lane, no branch.  Returns true when this lane needs a float64 decision for
 // it (the caller then redoes the whole block with the per-lane code; nothing of this call counts).
-struct MixedPair { float s, m, dx, dy, dz; bool exact; };
+struct MixedPair { float s, m, dx, dy, dz; bool in, exact; };
 
 // The parameter rows of a mixed system are laid out so that ONE formula serves both kinds
-// (k_force's prologue): a Boids-kind pair stores A = {r_sep, 0, -separation, 0}, B = {0, 0, 1, 1 / r_sep^2}
-// -- the Clusters profile then yields -separation inside r_sep and 0 outside, i.e. exactly the
-// Boids separation term once negated like every Clusters force -- and a Clusters-kind pair
-// B = {s1, f_max, 0, 0}: B.z is the 0 / 1 mask of the Boids sums, B.w = 1 / r_sep^2 marks the
-// separation radius whose edge needs a float64 decision (never matched when 0).
+// (k_force's prologue): a Clusters-kind pair stores A = {r_min^2, k0, f_min, mid}, B = {s1, f_max, 0, 0}
+// like the Clusters kernel, a Boids-kind pair A = {r_sep^2, 0, -separation, 0}, B = {0, 0, 1, 1 / r_sep^2}
+// -- clusters_scale then yields -separation / d inside r_sep and 0 outside, i.e. exactly the Boids
+// separation term once negated like every Clusters force.  B.z is the 0 / 1 mask of the Boids sums,
+// B.w = 1 / r_sep^2 marks the separation radius whose edge needs a float64 decision (never matched
+// when 0).
 template <bool LOWFIX>
 __device__ __forceinline__ MixedPair pair_mixed(RowAddr tabrow_s, const Geometry& g, const Image& im, const float4 pj)
 {
@@ -843,15 +843,10 @@ __device__ __forceinline__ MixedPair pair_mixed(RowAddr tabrow_s, const Geometry
     const unsigned at = tabrow_s.a + ((unsigned)__float_as_int(pj.w) << 4);
     const float4 qa = lds4(at);
     const float4 qb = lds4(at + kRowB);
-    const float inv = fast_rsqrt(d2);
-    const float dist = d2 * inv;
     const bool below = d2 < g.r2_lo;
-    const bool in = below && d2 > 1e-10f;
-    const float f_in = fmaf(-qa.y, dist, qa.z);
-    const float f_tri = fmaf(-qb.x, fabsf(dist - qa.w), qb.y);
-    const float sc = (dist < qa.x ? f_in : f_tri) * -inv;  // already negated: a += sc * d
-    r.s = in ? sc : 0.0f;
-    r.m = in ? qb.z : 0.0f;
+    r.in = below && d2 > 1e-10f;
+    r.s = clusters_scale(qa, make_float2(qb.x, qb.y), d2, fast_rsqrt(d2));
+    r.m = qb.z;
     r.dx = dx; r.dy = dy; r.dz = dz;
     // float64 decisions: the guard band of r_max^2, and -- in squared distances, a little wider than
     // the per-lane code's |dist - r_sep| < 4e-6 r_sep -- the edge of the separation radius
@@ -859,18 +854,22 @@ __device__ __forceinline__ MixedPair pair_mixed(RowAddr tabrow_s, const Geometry
     return r;
 }
 
+// (predicated, not masked: a pair out of range costs the issue slots of its ten multiply-adds but
+// no select in front of them; what it would have added is exactly zero either way)
 __device__ __forceinline__ void apply_mixed(Home& h, BoidRun& run, const MixedPair& r, const float4 vj)
 {
-    h.ax = fmaf(r.s, r.dx, h.ax);
-    h.ay = fmaf(r.s, r.dy, h.ay);
-    h.az = fmaf(r.s, r.dz, h.az);
-    run.c += r.m;
-    run.rx = fmaf(r.m, -r.dx, run.rx);
-    run.ry = fmaf(r.m, -r.dy, run.ry);
-    run.rz = fmaf(r.m, -r.dz, run.rz);
-    run.vx = fmaf(r.m, vj.x, run.vx);
-    run.vy = fmaf(r.m, vj.y, run.vy);
-    run.vz = fmaf(r.m, vj.z, run.vz);
+    if (r.in) {
+        h.ax = fmaf(-r.s, r.dx, h.ax);
+        h.ay = fmaf(-r.s, r.dy, h.ay);
+        h.az = fmaf(-r.s, r.dz, h.az);
+        run.c += r.m;
+        run.rx = fmaf(r.m, -r.dx, run.rx);
+        run.ry = fmaf(r.m, -r.dy, run.ry);
+        run.rz = fmaf(r.m, -r.dz, run.rz);
+        run.vx = fmaf(r.m, vj.x, run.vx);
+        run.vy = fmaf(r.m, vj.y, run.vy);
+        run.vz = fmaf(r.m, vj.z, run.vz);
+    }
 }
 
 // four survivors from the warp's lists (positions at `at`, velocities at `at_v`)
@@ -887,16 +886,21 @@ __device__ __forceinline__ void walk_group_mixed(Home& h, BoidRun& run, RowAddr 
         const float4 v0 = lds4v(at_v), v1 = lds4v(at_v + 16u), v2 = lds4v(at_v + 32u), v3 = lds4v(at_v + 48u);
         // the candidate's type is the same in every lane: a warp-uniform exchange of the running sums
         int t = __float_as_int(p0.w);
-        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+#ifdef GOF_EXP_NO_EXCHANGE
+#define GOF_XCHG(t) if (run.t < 0) boidrun_load(run, boid_acc, t)
+#else
+#define GOF_XCHG(t) if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+#endif
+        GOF_XCHG(t);
         apply_mixed(h, run, r0, v0);
         t = __float_as_int(p1.w);
-        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+        GOF_XCHG(t);
         apply_mixed(h, run, r1, v1);
         t = __float_as_int(p2.w);
-        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+        GOF_XCHG(t);
         apply_mixed(h, run, r2, v2);
         t = __float_as_int(p3.w);
-        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
+        GOF_XCHG(t);
         apply_mixed(h, run, r3, v3);
         return;
     }
@@ -922,7 +926,9 @@ __device__ __forceinline__ void walk_group_mixed(Home& h, BoidRun& run, RowAddr 
     }
 }
 
-// like walk_culled (not LITERAL): `lst` / `lst_v` = the warp's survivor lists (kListLen float4 each)
+// like walk_culled (not LITERAL): `lst` / `lst_v` = the warp's survivor lists (kListLen float4 each,
+// the velocities kListLen * 16 bytes behind the positions; linear, the < 4 waiting entries moved
+// to the front when the next chunk might not fit)
 template <bool LOWFIX>
 __device__ __forceinline__ void walk_culled_mixed(Home& h, BoidRun& run, RowAddr tabrow_s,
                                                   const PairParam* __restrict__ tabrow, float* __restrict__ boid_acc,
@@ -937,54 +943,69 @@ __device__ __forceinline__ void walk_culled_mixed(Home& h, BoidRun& run, RowAddr
     const float loy = b.loy + ty - g.cull_slack, hiy = b.hiy + ty + g.cull_slack;
     const float loz = b.loz + tz - g.cull_slack, hiz = b.hiz + tz + g.cull_slack;
     const unsigned lane = (unsigned)lane_id(), below = (1u << lane) - 1u;
-    unsigned head = 0u, len = 0u;  // warp-uniform; head stays a multiple of four
+    const unsigned dv = lst_v - lst;
+    unsigned head = 0u, tail = 0u;  // entries [head, tail) wait; warp-uniform; head is a multiple of four
     for (int base = s; base < e; base += 64) {
         const int j0 = base + (int)lane, j1 = j0 + 32;
-        bool keep0 = false, keep1 = false;
-        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-        if (j0 < e) p0 = ldg4(a.posw + j0);
-        if (j1 < e) p1 = ldg4(a.posw + j1);
+        const float4 p0 = ldg4(a.posw + min(j0, e - 1)), p1 = ldg4(a.posw + min(j1, e - 1));
         auto reach = [&](const float4 p) {
             const float ex = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
             const float ey = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
             const float ez = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
             return fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < g.cull_r2;
         };
-        if (j0 < e) keep0 = reach(p0);
-        if (j1 < e) keep1 = reach(p1);
+        const bool keep0 = reach(p0) && j0 < e, keep1 = reach(p1) && j1 < e;
+        if (tail + 64u > (unsigned)kListLen) {  // (warp-uniform, every third chunk of a run) make room
+            float4 w = p0, wv = p0;
+            const bool mine = lane < tail - head;
+            if (mine) {
+                w = lds4v(lst + ((head + lane) << 4));
+                wv = lds4v(lst_v + ((head + lane) << 4));
+            }
+            __syncwarp();
+            if (mine) {
+                sts4(lst + (lane << 4), w);
+                sts4(lst_v + (lane << 4), wv);
+            }
+            tail -= head;
+            head = 0u;
+        }
         const unsigned m0 = __ballot_sync(0xffffffffu, keep0), m1 = __ballot_sync(0xffffffffu, keep1);
         if (keep0) {
-            const unsigned at = (head + len + __popc(m0 & below)) & (kListLen - 1);
-            sts4(lst + (at << 4), p0);
-            sts4(lst_v + (at << 4), ldg4(a.veli + j0));
+            const unsigned at = lst + ((tail + __popc(m0 & below)) << 4);
+            sts4(at, p0);
+            sts4(at + dv, ldg4(a.veli + j0));
         }
         if (keep1) {
-            const unsigned at = (head + len + __popc(m0) + __popc(m1 & below)) & (kListLen - 1);
-            sts4(lst + (at << 4), p1);
-            sts4(lst_v + (at << 4), ldg4(a.veli + j1));
+            const unsigned at = lst + ((tail + __popc(m0) + __popc(m1 & below)) << 4);
+            sts4(at, p1);
+            sts4(at + dv, ldg4(a.veli + j1));
         }
-        len += __popc(m0) + __popc(m1);
+        tail += __popc(m0) + __popc(m1);
         __syncwarp();
-        while (len >= 4u) {
-            const unsigned at = (head & (kListLen - 1)) << 4;
-            walk_group_mixed<LOWFIX>(h, run, tabrow_s, tabrow, boid_acc, a, g, im, lst + at, lst_v + at);
-            head += 4u;
-            len -= 4u;
+        const unsigned stop = tail & ~3u;
+        if (stop != head) {
+            unsigned at = lst + (head << 4);
+            const unsigned end = lst + (stop << 4);
+            do {
+                walk_group_mixed<LOWFIX>(h, run, tabrow_s, tabrow, boid_acc, a, g, im, at, at + dv);
+                at += 64u;
+            } while (at != end);
+            head = stop;
         }
-        __syncwarp();  // the lists are read before the next chunk appends to them
     }
-    if (len > 0u) {
-        if (lane < 4u - len) {
+    if (tail != head) {
+        if (lane < 4u - (tail - head)) {
             // (type 0 and zero velocity: the parked particle is out of everybody's range)
-            const unsigned at = (head + len + lane) & (kListLen - 1);
-            sts4(lst + (at << 4), make_float4(kDummyPos, kDummyPos, kDummyPos, 0.0f));
-            sts4(lst_v + (at << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+            const unsigned at = lst + ((tail + lane) << 4);
+            sts4(at, make_float4(kDummyPos, kDummyPos, kDummyPos, 0.0f));
+            sts4(at + dv, make_float4(0.f, 0.f, 0.f, 0.f));
         }
         __syncwarp();
-        const unsigned at = (head & (kListLen - 1)) << 4;
-        walk_group_mixed<LOWFIX>(h, run, tabrow_s, tabrow, boid_acc, a, g, im, lst + at, lst_v + at);
-        __syncwarp();
+        const unsigned at = lst + (head << 4);
+        walk_group_mixed<LOWFIX>(h, run, tabrow_s, tabrow, boid_acc, a, g, im, at, at + dv);
     }
+    __syncwarp();  // the lists are read before the next run appends to them
     h.ax += ax0; h.ay += ay0; h.az += az0;
 }
 
@@ -1409,9 +1430,9 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
         tab[q] = pp;
         const int r = q / T, c = q - r * T;
         float4 ea = pp.a, eb = make_float4(pp.b.x, pp.b.y, 0.0f, 0.0f);
-        if (KIND == kKindClusters) ea.x = pp.a.x * pp.a.x;  // clusters_scale compares squared distances
+        ea.x = pp.a.x * pp.a.x;  // clusters_scale compares squared distances
         if (KIND == kKindMixed && ((a.kind_rows[r] >> c) & 1u)) {  // Boids-kind pair: see pair_mixed
-            ea = make_float4(pp.a.x, 0.0f, -pp.a.y, 0.0f);
+            ea = make_float4(pp.a.x * pp.a.x, 0.0f, -pp.a.y, 0.0f);
             eb = make_float4(0.0f, 0.0f, 1.0f, 1.0f / (pp.a.x * pp.a.x));
         }
         *reinterpret_cast<float4*>(tabAB + r * kRowBytes + c * 16) = ea;
