@@ -824,17 +824,19 @@ __device__ __forceinline__ void boidrun_load(BoidRun& r, const float* __restrict
 
 // One survivor, every lane, no branch.  Returns true when this lane needs a float64 decision for
 // it (the caller then redoes the whole block with the per-lane code; nothing of this call counts).
-struct MixedPair { float s, m, dx, dy, dz; bool in, exact; };
+struct MixedPair { float s, dx, dy, dz; bool in, sums, exact; };
 
 // The parameter rows of a mixed system are laid out so that ONE formula serves both kinds
-// (k_force's prologue): a Clusters-kind pair stores A = {r_min^2, k0, f_min, mid}, B = {s1, f_max, 0, 0}
-// like the Clusters kernel, a Boids-kind pair A = {r_sep^2, 0, -separation, 0}, B = {0, 0, 1, 1 / r_sep^2}
-// -- clusters_scale then yields -separation / d inside r_sep and 0 outside, i.e. exactly the Boids
-// separation term once negated like every Clusters force.  B.z is the 0 / 1 mask of the Boids sums,
-// B.w = 1 / r_sep^2 marks the separation radius whose edge needs a float64 decision (never matched
-// when 0).
+// (k_force's prologue): a Clusters-kind pair stores A = {r_min^2, k0, f_min, mid}, B = {s1, f_max}
+// like the Clusters kernel, a Boids-kind pair A = {r_sep^2, 0, -separation, 0}, B = {0, 0} --
+// clusters_scale then yields -separation / d inside r_sep and 0 outside, i.e. exactly the Boids
+// separation term once negated like every Clusters force.  Whether the pair also counts for the
+// lane's per-type sums is bit t of the home species' kinds row (a register), not another table
+// word: the walk is bound by shared-memory wavefronts, and 24 bytes of parameters per lane and
+// candidate are six of them where 32 were eight.
 template <bool LOWFIX>
-__device__ __forceinline__ MixedPair pair_mixed(RowAddr tabrow_s, const Geometry& g, const Image& im, const float4 pj)
+__device__ __forceinline__ MixedPair pair_mixed(unsigned kinds, RowAddr tabrow_s, const Geometry& g, const Image& im,
+                                                const float4 pj)
 {
     MixedPair r;
     float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
@@ -842,33 +844,33 @@ __device__ __forceinline__ MixedPair pair_mixed(RowAddr tabrow_s, const Geometry
     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     const unsigned at = tabrow_s.a + ((unsigned)__float_as_int(pj.w) << 4);
     const float4 qa = lds4(at);
-    const float4 qb = lds4(at + kRowB);
+    const float2 qb = lds2(at + kRowB);
     const bool below = d2 < g.r2_lo;
     r.in = below && d2 > 1e-10f;
-    r.s = clusters_scale(qa, make_float2(qb.x, qb.y), d2, fast_rsqrt(d2));
-    r.m = qb.z;
+    r.sums = r.in && ((kinds >> __float_as_int(pj.w)) & 1u);
+    r.s = clusters_scale(qa, qb, d2, fast_rsqrt(d2));
     r.dx = dx; r.dy = dy; r.dz = dz;
     // float64 decisions: the guard band of r_max^2, and -- in squared distances, a little wider than
-    // the per-lane code's |dist - r_sep| < 4e-6 r_sep -- the edge of the separation radius
-    r.exact = (!below && d2 < g.r2_hi) || fabsf(fmaf(d2, qb.w, -1.0f)) < 1e-5f;
+    // the per-lane code's |dist - r_sep| < 4e-6 r_sep -- the edge of the radius in qa.x (the
+    // separation radius of a Boids-kind pair; for a Clusters-kind pair it is r_min, where nothing
+    // has to be decided, but a flag there is as rare and costs nothing else)
+    r.exact = (!below && d2 < g.r2_hi) || fabsf(d2 - qa.x) < 1e-5f * qa.x;
     return r;
 }
 
-// (predicated, not masked: a pair out of range costs the issue slots of its ten multiply-adds but
-// no select in front of them; what it would have added is exactly zero either way)
+// (predicated, not masked: a pair out of range costs the issue slots of its ten additions but no
+// select in front of them; what it would have added is exactly zero either way)
 __device__ __forceinline__ void apply_mixed(Home& h, BoidRun& run, const MixedPair& r, const float4 vj)
 {
     if (r.in) {
         h.ax = fmaf(-r.s, r.dx, h.ax);
         h.ay = fmaf(-r.s, r.dy, h.ay);
         h.az = fmaf(-r.s, r.dz, h.az);
-        run.c += r.m;
-        run.rx = fmaf(r.m, -r.dx, run.rx);
-        run.ry = fmaf(r.m, -r.dy, run.ry);
-        run.rz = fmaf(r.m, -r.dz, run.rz);
-        run.vx = fmaf(r.m, vj.x, run.vx);
-        run.vy = fmaf(r.m, vj.y, run.vy);
-        run.vz = fmaf(r.m, vj.z, run.vz);
+    }
+    if (r.sums) {
+        run.c += 1.0f;
+        run.rx -= r.dx; run.ry -= r.dy; run.rz -= r.dz;
+        run.vx += vj.x; run.vy += vj.y; run.vz += vj.z;
     }
 }
 
@@ -880,27 +882,22 @@ __device__ __forceinline__ void walk_group_mixed(Home& h, BoidRun& run, RowAddr 
                                                  unsigned at_v)
 {
     const float4 p0 = lds4v(at), p1 = lds4v(at + 16u), p2 = lds4v(at + 32u), p3 = lds4v(at + 48u);
-    const MixedPair r0 = pair_mixed<LOWFIX>(tabrow_s, g, im, p0), r1 = pair_mixed<LOWFIX>(tabrow_s, g, im, p1),
-                    r2 = pair_mixed<LOWFIX>(tabrow_s, g, im, p2), r3 = pair_mixed<LOWFIX>(tabrow_s, g, im, p3);
+    const MixedPair r0 = pair_mixed<LOWFIX>(h.kinds, tabrow_s, g, im, p0), r1 = pair_mixed<LOWFIX>(h.kinds, tabrow_s, g, im, p1),
+                    r2 = pair_mixed<LOWFIX>(h.kinds, tabrow_s, g, im, p2), r3 = pair_mixed<LOWFIX>(h.kinds, tabrow_s, g, im, p3);
     if (!__any_sync(0xffffffffu, r0.exact | r1.exact | r2.exact | r3.exact)) {
         const float4 v0 = lds4v(at_v), v1 = lds4v(at_v + 16u), v2 = lds4v(at_v + 32u), v3 = lds4v(at_v + 48u);
         // the candidate's type is the same in every lane: a warp-uniform exchange of the running sums
         int t = __float_as_int(p0.w);
-#ifdef GOF_EXP_NO_EXCHANGE
-#define GOF_XCHG(t) if (run.t < 0) boidrun_load(run, boid_acc, t)
-#else
-#define GOF_XCHG(t) if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
-#endif
-        GOF_XCHG(t);
+        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
         apply_mixed(h, run, r0, v0);
         t = __float_as_int(p1.w);
-        GOF_XCHG(t);
+        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
         apply_mixed(h, run, r1, v1);
         t = __float_as_int(p2.w);
-        GOF_XCHG(t);
+        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
         apply_mixed(h, run, r2, v2);
         t = __float_as_int(p3.w);
-        GOF_XCHG(t);
+        if (t != run.t) { boidrun_store(run, boid_acc); boidrun_load(run, boid_acc, t); }
         apply_mixed(h, run, r3, v3);
         return;
     }
@@ -1433,7 +1430,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
         ea.x = pp.a.x * pp.a.x;  // clusters_scale compares squared distances
         if (KIND == kKindMixed && ((a.kind_rows[r] >> c) & 1u)) {  // Boids-kind pair: see pair_mixed
             ea = make_float4(pp.a.x * pp.a.x, 0.0f, -pp.a.y, 0.0f);
-            eb = make_float4(0.0f, 0.0f, 1.0f, 1.0f / (pp.a.x * pp.a.x));
+            eb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         *reinterpret_cast<float4*>(tabAB + r * kRowBytes + c * 16) = ea;
         *reinterpret_cast<float4*>(tabAB + r * kRowBytes + kRowB + c * 16) = eb;
