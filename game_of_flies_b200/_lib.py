@@ -68,6 +68,8 @@ SIGNATURES = {
     "gof_engine_step": (_i, [_vp, _i, _f, _i, _vp]),
     "gof_engine_accelerate": (_i, [_vp, _i, _vp]),
     "gof_engine_download": (_i, [_vp] + [_vp] * 9 + [_vp]),
+    "gof_engine_step_host": (_i, [_vp, _vp, _vp, _vp, _f, _i, _vp]),
+    "gof_engine_host_wait": (_i, [_vp]),
     "gof_engine_snapshot": (_i, [_vp, _vp, _vp]),
     "gof_engine_snapshot_stage": (_i, [_vp, _vp]),
     "gof_engine_snapshot_copy": (_i, [_vp, _vp, _vp]),

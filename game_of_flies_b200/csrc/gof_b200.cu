@@ -829,6 +829,14 @@ struct gof_engine {
     int* stage_bins = nullptr;     // particle_bins / particle_indices export
     int* stage_indices = nullptr;
     float* stage_xyz = nullptr;    // snapshot [N][3]
+    // gof_engine_step_host: a second SoA staging set for the way back, so that the next call's
+    // uploads can run while this call's downloads are still leaving
+    float* stage_down[9] = {};
+    cudaStream_t host_side = nullptr;          // the downloads' stream
+    cudaEvent_t ev_ready = nullptr;            // un-permuted state staged
+    cudaEvent_t ev_down[9] = {};               // download k of the last call complete
+    const void* down_ptr[9] = {};              // ... and where it goes
+    bool down_pending = false;
 
     // slab mode (multi-GPU): this engine owns the global z-layers [layer_lo, layer_hi)
     bool slab = false;
@@ -917,6 +925,8 @@ static size_t engine_layout(gof_engine* e, char* base)
     e->stage_bins = (int*)take(cap * sizeof(int));
     e->stage_indices = (int*)take(cap * sizeof(int));
     e->stage_xyz = (float*)take(cap * 3 * sizeof(float));
+    if (!e->slab)
+        for (int k = 0; k < 9; ++k) e->stage_down[k] = (float*)take(cap * sizeof(float));
     if (e->slab) {
         for (int d = 0; d < 2; ++d) {
             e->mig_send[d] = (float4*)take(((size_t)e->mig_capacity * 3 + 1) * sizeof(float4));
@@ -965,6 +975,13 @@ extern "C" void gof_engine_destroy(gof_engine* e)
     for (auto& g : e->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
+    if (e->host_side) {
+        cudaStreamSynchronize(e->host_side);
+        cudaStreamDestroy(e->host_side);
+    }
+    if (e->ev_ready) cudaEventDestroy(e->ev_ready);
+    for (cudaEvent_t v : e->ev_down)
+        if (v) cudaEventDestroy(v);
     delete e;
 }
 
@@ -1255,6 +1272,68 @@ extern "C" int gof_engine_download(gof_engine* e, float* px, float* py, float* p
     float* dst[9] = {px, py, pz, vx, vy, vz, ax, ay, az};
     for (int k = 0; k < 9; ++k)
         if (dst[k]) GOF_CUDA(cudaMemcpyAsync(dst[k], e->stage[k], (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    return 0;
+}
+
+/* One step of a host-driven loop with the transfers in both directions at once (see the header). */
+extern "C" int gof_engine_step_host(gof_engine* e, const float* const* in9, const int32_t* types,
+                                    float* const* out9, float timestep, int wrap_mode, void* stream)
+{
+    DeviceGuard guard(e ? e->device : -1);
+    if (int rc = engine_ready(e, false)) return rc;
+    if (e->slab) return fail(GOF_E_STATE, "gof_engine_step_host: not available on a slab engine");
+    if (!in9 || !out9 || !types) return fail(GOF_E_INVALID, "gof_engine_step_host: null argument");
+    for (int k = 0; k < 9; ++k)
+        if (!in9[k] || !out9[k]) return fail(GOF_E_INVALID, "gof_engine_step_host: all nine arrays are required both ways");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!e->host_side) {
+        GOF_CUDA(cudaStreamCreateWithFlags(&e->host_side, cudaStreamNonBlocking));
+        GOF_CUDA(cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming));
+        for (int k = 0; k < 9; ++k) GOF_CUDA(cudaEventCreateWithFlags(&e->ev_down[k], cudaEventDisableTiming));
+    }
+    const int n = e->capacity;
+    // uploads: an array that the previous call is still downloading into waits for exactly that copy
+    for (int k = 0; k < 9; ++k) {
+        if (e->down_pending)
+            for (int m = 0; m < 9; ++m)
+                if (e->down_ptr[m] == (const void*)in9[k]) GOF_CUDA(cudaStreamWaitEvent(st, e->ev_down[m], 0));
+        GOF_CUDA(cudaMemcpyAsync(e->stage[k], in9[k], (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    }
+    GOF_CUDA(cudaMemcpyAsync(e->stage_types, types, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
+    if (e->species_dirty) {
+        if (int rc = upload_species(e->species, e->dspecies, st)) return rc;
+        e->species_dirty = false;
+    }
+    GOF_CUDA(cudaMemsetAsync(e->scalars, 0, sizeof(StepScalars), st));
+    e->parity = 0;
+    e->n = n;
+    GOF_LAUNCH(k_pack, cdiv(n, kEwThreads), kEwThreads, 0, st, e->stage[0], e->stage[1], e->stage[2], e->stage[3],
+               e->stage[4], e->stage[5], e->stage[6], e->stage[7], e->stage[8], e->stage_types, n, e->posw[0],
+               e->veli[0], e->acc, &e->scalars->max_sq_speed_bits[0]);
+    e->uploaded = true;
+    e->binned = false;
+    if (int rc = gof_engine_step(e, 1, timestep, wrap_mode, stream)) return rc;
+    // the way back: un-permute into the second staging set once the previous call's copies have left it
+    if (e->down_pending) GOF_CUDA(cudaStreamWaitEvent(st, e->ev_down[8], 0));
+    GOF_LAUNCH(k_unpack, cdiv(n, kEwThreads), kEwThreads, 0, st, e->posw[0], e->veli[0], e->acc, n, e->stage_down[0],
+               e->stage_down[1], e->stage_down[2], e->stage_down[3], e->stage_down[4], e->stage_down[5],
+               e->stage_down[6], e->stage_down[7], e->stage_down[8]);
+    GOF_CUDA(cudaEventRecord(e->ev_ready, st));
+    GOF_CUDA(cudaStreamWaitEvent(e->host_side, e->ev_ready, 0));
+    for (int k = 0; k < 9; ++k) {
+        GOF_CUDA(cudaMemcpyAsync(out9[k], e->stage_down[k], (size_t)n * sizeof(float), cudaMemcpyDefault, e->host_side));
+        GOF_CUDA(cudaEventRecord(e->ev_down[k], e->host_side));
+        e->down_ptr[k] = out9[k];
+    }
+    e->down_pending = true;
+    return 0;
+}
+
+extern "C" int gof_engine_host_wait(gof_engine* e)
+{
+    if (!e) return fail(GOF_E_INVALID, "null engine");
+    DeviceGuard guard(e->device);
+    if (e->down_pending) GOF_CUDA(cudaEventSynchronize(e->ev_down[8]));
     return 0;
 }
 

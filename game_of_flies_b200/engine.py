@@ -124,6 +124,24 @@ class ParticleEngine:
             ptrs += [_any_ptr(a) for a in grp] if grp is not None else [0, 0, 0]
         _lib.check(self.lib.gof_engine_download(self._handle, *ptrs, self._stream()))
 
+    def step_host(self, state_in, types, state_out, timestep=None):
+        """One step of a host-driven loop (gof_engine_step_host): `state_in` / `state_out` are nine
+        fp32 buffers each (pos xyz, vel xyz, acc xyz; pinned CPU tensors, numpy arrays or CUDA
+        tensors).  Uploads and step on the current stream, downloads on the engine's own stream;
+        consecutive calls that use two sets of buffers alternately overlap their transfers.
+        Returns at once: host_wait() before reading `state_out`."""
+        assert len(state_in) == 9 and len(state_out) == 9
+        arr = C.c_void_p * 9
+        ins = arr(*[_any_ptr(a) for a in state_in])
+        outs = arr(*[_any_ptr(a) for a in state_out])
+        ts = -1.0 if timestep is None else float(timestep)
+        _lib.check(self.lib.gof_engine_step_host(self._handle, ins, _any_ptr(types), outs, ts, self.wrap_mode,
+                                                 self._stream()))
+
+    def host_wait(self):
+        """Block until the downloads of the last step_host are complete."""
+        _lib.check(self.lib.gof_engine_host_wait(self._handle))
+
     def snapshot_into(self, xyz):
         """Positions as [N][3] fp32 into a pinned tensor / numpy array / CUDA tensor (async)."""
         _lib.check(self.lib.gof_engine_snapshot(self._handle, _any_ptr(xyz), self._stream()))

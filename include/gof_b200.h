@@ -172,6 +172,21 @@ int gof_engine_download(gof_engine *e, float *pos_x_any, float *pos_y_any, float
                         float *vel_x_any, float *vel_y_any, float *vel_z_any, float *acc_x_any,
                         float *acc_y_any, float *acc_z_any, void *stream);
 
+/* One step of a HOST-driven loop: upload the state from nine host (or device) arrays, one
+ * core_step, download the new state into nine arrays -- what a caller does who keeps the state
+ * on the host between steps, as main/simulation.py does between `cuda.to_device`
+ * (simulation.py:161-173) and `copy_to_host` (:295-304).  The uploads and the step run on
+ * `stream`, the downloads on a stream of the engine's own, so that in a loop whose next input is
+ * this call's output (two sets of host buffers used alternately) array k of the next call goes up
+ * while array k + 1 of this call still comes down: both directions of the link are busy.  The
+ * dependencies are tracked by host pointer: an input array that the previous call is still
+ * writing waits for exactly that copy.  The call returns at once; gof_engine_host_wait blocks
+ * until the outputs of the last call are complete.  pos/vel/acc xyz in the order of
+ * gof_engine_upload; all nine are required both ways.  Not for slab engines. */
+int gof_engine_step_host(gof_engine *e, const float *const *in9_any, const int32_t *types_any,
+                         float *const *out9_any, float timestep, int wrap_mode, void *stream);
+int gof_engine_host_wait(gof_engine *e);
+
 /* Simulation.update's host copy (main/simulation.py:295-304): positions as [N][3]
  * fp32 in particle order.  xyz_any is typically pinned host memory; the copy is
  * asynchronous on `stream`. */

@@ -418,6 +418,46 @@ def test_recorder_pipeline_writes_the_same_frames_as_stepwise_updates(gof, tmp_p
     assert np.array_equal(state["type_array"][: int(state["num_particles"])], a.particle_type_index_array)
 
 
+@pytest.mark.parametrize("kinds", ["clusters", "mixed"])
+@pytest.mark.parametrize("two_buffer_sets", [True, False])
+def test_host_driven_loop_with_overlapped_transfers_equals_stepwise(gof, kinds, two_buffer_sets):
+    """gof_engine_step_host (uploads on the caller's stream, downloads on the engine's own, the next
+    call's uploads ordered behind the copies into the buffers they read) must give, step for step,
+    what upload + step + download with a synchronisation after every call gives -- whether the loop
+    alternates two sets of host buffers or reads and writes one."""
+    import torch
+    st = random_state([1500, 1200, 900, 800], (70.0, 60.0, 80.0), 77, kinds=kinds, speed=2.0)
+    n = st["n"]
+    start = [st[g][k].astype(np.float32) for g in ("pos", "vel", "acc") for k in range(3)]
+    types = torch.from_numpy(st["types"].astype(np.int32)).pin_memory()
+    # reference: synchronous calls, state carried by the host
+    a = gof.eng.ParticleEngine(n, st["parameter_matrix"], st["limits"], st["r_max"])
+    cur = [x.copy() for x in start]
+    want = []
+    for _ in range(6):
+        a.upload(cur[0:3], st["types"], vel=cur[3:6], acc=cur[6:9])
+        a.step(1)
+        d = a.download(pos=True, vel=True, acc=True)
+        cur = [d[g][k].copy() for g in ("pos", "vel", "acc") for k in range(3)]
+        want.append([x.copy() for x in cur])
+    a.close()
+    # the pipelined loop
+    b = gof.eng.ParticleEngine(n, st["parameter_matrix"], st["limits"], st["r_max"])
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    sets = [[pin(x) for x in start], [pin(np.zeros(n, np.float32)) for _ in range(9)]]
+    got = []
+    for k in range(6):
+        src, dst = (sets[k & 1], sets[(k & 1) ^ 1]) if two_buffer_sets else (sets[0], sets[0])
+        b.step_host(src, types, dst)
+        if k in (2, 5):  # look at the host buffers only where the loop waits
+            b.host_wait()
+            got.append((k, [t.numpy().copy() for t in dst]))
+    b.close()
+    for k, arrs in got:
+        for q in range(9):
+            assert np.array_equal(arrs[q], want[k][q]), (k, q)
+
+
 def check_full_field(gof, st, wrap_mode, label):
     """Whole-system parity at a BASELINE size: every particle's bin, the bin tables, the sorted
     order and the whole acceleration field of the state, then one full step, against the oracle
