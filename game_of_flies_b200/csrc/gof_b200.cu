@@ -404,7 +404,10 @@ static int launch_force_m(const Geometry& g, const ForceArgs& a, int kind, cudaS
         return launch_force_t<kKindBoids, MODE, 1>(g, a, st);
     }
     if (kind == kKindMixed) return launch_force_t<kKindMixed, MODE, 1>(g, a, st);
-    switch (pick_split(g, a.home_count + a.home_count2, false)) {
+    // (a slab launches its interior and its two boundary layers apart, side by side: what decides
+    // whether the GPU is full is the slab's population, not the 5 % of it in the boundary launch --
+    // which used to get the 9-warp kernel of small systems, three times the SM time per particle)
+    switch (pick_split(g, a.split_homes > 0 ? a.split_homes : a.home_count + a.home_count2, false)) {
         case 9: return launch_force_t<kKindClusters, MODE, 9>(g, a, st);
         case 3: return launch_force_t<kKindClusters, MODE, 3>(g, a, st);
         default: return launch_force_t<kKindClusters, MODE, 1>(g, a, st);
@@ -1151,6 +1154,7 @@ static void engine_force_args(gof_engine* e, int wrap_mode, ForceArgs* a)
     a->scalars = e->scalars;
     a->n_total = e->n;
     a->slot_limit = e->slot_capacity;
+    a->split_homes = e->slab ? e->capacity : 0;  // (a slab's launches cover parts of it: see launch_force_m)
 }
 
 // the launches of one core_step at the engine's current parity (which the caller flips)

@@ -87,6 +87,7 @@ struct ForceArgs {
     int n_total;
     int slot_limit;           // upper bound of the indices into posw / veli (Boids-kind queue entries)
     int wave_sms;             // SMs of the device (placement of the literal z-wrap blocks in the first wave)
+    int split_homes;          // host side only: the population that decides the row split (0: this launch's)
 };
 
 // Per-thread state of the particle being updated.
