@@ -590,6 +590,15 @@ def main():
         launches = int(lib.gof_launch_count())
         force_ms, force_launches = eng.force_time()
         phases = eng.phase_times() if hasattr(eng, "phase_times") else None
+        phases_all = None
+        if world > 1 and phases and phases.get("steps"):
+            # every rank's phases (a step ends when the slowest slab is done: the next timestep needs
+            # every slab's maximum speed)
+            mine = torch.tensor([phases["prefix"], phases["interior_forces"], phases["halo_and_boundary_forces"],
+                                 phases["step"]], dtype=torch.float64, device=device)
+            allp = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allp, mine)
+            phases_all = [[round(float(v), 4) for v in t.tolist()] for t in allp]
         eng.timing(False)
         # a timed region of a few tens of milliseconds ends before nvidia-smi's next sample: keep the
         # same load on (untimed) until there are at least three samples per GPU, at most ~1.5 s
@@ -606,6 +615,7 @@ def main():
         clocks = sampler.stop() if sampler else None
         stats = eng.pair_stats() if hasattr(eng, "pair_stats") else None
         out = {"hs": hs, "ms_total": ms_total, "launches": launches, "force_ms": force_ms, "phases": phases,
+               "phases_all": phases_all,
                "force_launches": force_launches, "clocks": clocks, "stats": stats,
                "value": world * n * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps}
         # ---- end to end through the public API with host buffers --------------------------
@@ -749,6 +759,9 @@ def main():
         }
         if res.get("phases") and res["phases"]["steps"]:
             line["slab_phases_ms_per_step"] = res["phases"]  # (rank 0's slab; peer-memory transport)
+            if res.get("phases_all"):
+                line["slab_phases_all_ranks"] = {"columns": ["prefix", "interior_forces", "halo_and_boundary_forces", "step"],
+                                                 "ms_per_step": res["phases_all"]}
         if "steady" in res:
             line["steady_state"] = res["steady"]
         if parity is not None:
