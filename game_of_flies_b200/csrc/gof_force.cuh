@@ -27,7 +27,10 @@
 
 namespace gof {
 
-constexpr int kForceThreads = 128;
+#ifndef GOF_FORCE_THREADS
+#define GOF_FORCE_THREADS 128
+#endif
+constexpr int kForceThreads = GOF_FORCE_THREADS;  // home particles per block (SPLIT == 1)
 constexpr int kBoidSlots = 8;  // per partner type, two float4: {count, sum of relative positions}, {sum of velocities, -}
 
 // The per-type sums of a thread live in shared memory as float4 pairs: vector v (0 / 1) of partner
