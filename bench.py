@@ -415,6 +415,9 @@ def main():
     ap.add_argument("--density", type=float, default=None)
     ap.add_argument("--seed", type=int, default=434)
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-systems", type=int, default=3,
+                    help="one GPU: independent systems driven from the host in turn in the end-to-end leg "
+                         "(1: a single system, every step waits for its own round trip over PCIe)")
     ap.add_argument("--evolve", type=int, default=300,
                     help="steps to evolve before the steady-state timing (0: skip it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -514,6 +517,45 @@ def main():
                 eng.host_wait()
                 torch.cuda.current_stream(device).synchronize()
             e2e_step.pipelined = e2e_pipelined
+
+            systems = []  # [engine, stream, [in set, out set]] per interleaved system
+
+            def e2e_interleaved(k, count):
+                """`count` independent systems driven from the host in turn (the batch path of the
+                reference renders many simulations): each keeps its own host-driven loop -- every
+                step uploads that system's state from pinned host memory, steps, downloads it into
+                the buffers its next step starts from (gof_engine_step_host) -- on its own stream, so
+                that the copies of one system run under the kernels of another.  One host wait per
+                system at the end."""
+                if not systems:
+                    for s in range(count):
+                        if s == 0:
+                            e, sets = eng, [bufs["in"], bufs["out"]]
+                        else:
+                            e = ParticleEngine(n, hs["parameter_matrix"], hs["limits"], float(hs["r_max"]),
+                                               device=device, wrap_mode=wrap_mode)
+                            sets = [tuple([t.clone().pin_memory() for t in grp] for grp in bufs["in"]),
+                                    tuple([torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(3)]
+                                          for _ in range(3))]
+                        systems.append([e, torch.cuda.Stream(device), sets])
+                    torch.cuda.synchronize(device)
+                for _ in range(k):
+                    for sy in systems:
+                        e, st, sets = sy
+                        (p, v, a), (op, ov, oa) = sets
+                        with torch.cuda.stream(st):
+                            e.step_host([*p, *v, *a], h_types, [*op, *ov, *oa], args.timestep)
+                        sy[2] = [sets[1], sets[0]]
+                for e, st, _ in systems:
+                    e.host_wait()
+                    st.synchronize()
+
+            def close_systems():
+                for e, _, _ in systems[1:]:
+                    e.close()
+                systems.clear()
+            e2e_step.interleaved = e2e_interleaved
+            e2e_step.close = close_systems
             return hs, eng, None, step, e2e_step
         # ---- several GPUs: z-slab decomposition, one slab per rank, weak scaling ---------------
         from game_of_flies_b200.slab import SlabEngine, make_runner
@@ -637,6 +679,14 @@ def main():
                 barrier()
                 out["e2e_sync_value"] = out["e2e_value"]
                 out["e2e_value"] = world * n * e2e_steps / (time.perf_counter() - t0)
+                if args.e2e_systems > 1:  # several independent systems, each in its own host-driven loop
+                    e2e_step.interleaved(2, args.e2e_systems)
+                    barrier()
+                    t0 = time.perf_counter()
+                    e2e_step.interleaved(e2e_steps, args.e2e_systems)
+                    barrier()
+                    out["e2e_interleaved_value"] = world * n * e2e_steps * args.e2e_systems / (time.perf_counter() - t0)
+                    e2e_step.close()
         # ---- steady state: the same system after it has clumped ---------------------------
         if evolve > 0:
             # (the end-to-end steps above left the state `e2e_steps` further on; the count below is
@@ -757,6 +807,15 @@ def main():
             "gpu_launches": res["launches"],
             "roofline": roofline,
         }
+        if res.get("e2e_interleaved_value"):
+            # not the headline `e2e.value` (one system, every step waits for its own round trip over
+            # PCIe): what the link and the GPU sustain when the host drives several systems in turn
+            line["e2e"]["interleaved_systems"] = {
+                "systems": args.e2e_systems, "value": res["e2e_interleaved_value"], "unit": "particle-updates/s",
+                "what": (f"{args.e2e_systems} independent systems of N particles driven from the host in turn, each "
+                         "in its own loop of gof_engine_step_host calls on its own stream (every step of every "
+                         "system uploads its state from pinned host memory and downloads it into the buffers its "
+                         "next step starts from): the copies of one system run under the kernels of another")}
         if res.get("phases") and res["phases"]["steps"]:
             line["slab_phases_ms_per_step"] = res["phases"]  # (rank 0's slab; peer-memory transport)
             if res.get("phases_all"):
