@@ -458,6 +458,46 @@ def test_host_driven_loop_with_overlapped_transfers_equals_stepwise(gof, kinds, 
             assert np.array_equal(arrs[q], want[k][q]), (k, q)
 
 
+def test_interleaved_host_driven_systems_equal_their_own_loops(gof):
+    """bench.py's `e2e.interleaved_systems`: several independent systems, each in its own loop of
+    gof_engine_step_host calls on its own stream (the copies of one run under the kernels of
+    another), must each come out exactly as when it is stepped alone with synchronous calls."""
+    import torch
+    states = [random_state([900, 700, 800], (60.0, 70.0, 50.0), 31 + s, kinds="clusters" if s != 1 else "mixed",
+                           speed=2.0) for s in range(3)]
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    want = []
+    for st in states:
+        a = gof.eng.ParticleEngine(st["n"], st["parameter_matrix"], st["limits"], st["r_max"])
+        cur = [st[g][k].astype(np.float32) for g in ("pos", "vel", "acc") for k in range(3)]
+        for _ in range(5):
+            a.upload(cur[0:3], st["types"], vel=cur[3:6], acc=cur[6:9])
+            a.step(1)
+            d = a.download(pos=True, vel=True, acc=True)
+            cur = [d[g][k].copy() for g in ("pos", "vel", "acc") for k in range(3)]
+        want.append(cur)
+        a.close()
+    systems = []
+    for st in states:
+        e = gof.eng.ParticleEngine(st["n"], st["parameter_matrix"], st["limits"], st["r_max"])
+        start = [st[g][k].astype(np.float32) for g in ("pos", "vel", "acc") for k in range(3)]
+        sets = [[pin(x) for x in start], [pin(np.zeros(st["n"], np.float32)) for _ in range(9)]]
+        systems.append([e, torch.cuda.Stream(), sets, pin(st["types"].astype(np.int32))])
+    torch.cuda.synchronize()
+    for _ in range(5):
+        for sy in systems:
+            e, stream, sets, types = sy
+            with torch.cuda.stream(stream):
+                e.step_host(sets[0], types, sets[1])
+            sy[2] = [sets[1], sets[0]]
+    for s, (e, stream, sets, _) in enumerate(systems):
+        e.host_wait()
+        stream.synchronize()
+        for q in range(9):
+            assert np.array_equal(sets[0][q].numpy(), want[s][q]), (s, q)
+        e.close()
+
+
 def check_full_field(gof, st, wrap_mode, label):
     """Whole-system parity at a BASELINE size: every particle's bin, the bin tables, the sorted
     order and the whole acceleration field of the state, then one full step, against the oracle
