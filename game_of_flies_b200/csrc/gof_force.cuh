@@ -411,6 +411,9 @@ __device__ __noinline__ float3 queue_drain(float3 f, unsigned qbase, int count, 
         const int j = (int)(entry & ((1u << kQueueSlotBits) - 1u));
         const int shifts = (int)(entry >> kQueueSlotBits);
         const float4 pj = ldg4(a.posw + j);
+        // the velocity is requested together with the position (a queued pair all but always
+        // interacts): one round trip to L2 per entry instead of two dependent ones
+        const float4 vj = ldg4(a.veli + j);
         float dx = hx - pj.x, dy = hy - pj.y, dz = hz - pj.z;
         if (shifts != pack_shifts(0, 0, 0)) {  // met across a periodic boundary (home cells on the box faces)
             const Image im = make_image(h, g, (shifts & 3) - 1, ((shifts >> 2) & 3) - 1, ((shifts >> 4) & 3) - 1);
@@ -424,7 +427,7 @@ __device__ __noinline__ float3 queue_drain(float3 f, unsigned qbase, int count, 
         }
         if (ok)
             interact<true>(h, tabrow, boid_acc, a, a.T, j, __float_as_int(pj.w), dx, dy, dz, -dx, -dy, -dz, d2,
-                           [&]() { return exact_dist2(g, hx, hy, hz, pj.x, pj.y, pj.z, shifts); });
+                           [&]() { return exact_dist2(g, hx, hy, hz, pj.x, pj.y, pj.z, shifts); }, &vj);
     }
     return make_float3(h.ax, h.ay, h.az);
 }
