@@ -360,11 +360,24 @@ __device__ __forceinline__ void repair(float3& rep, const Home& h, const PairPar
 #endif
 constexpr int kQueueDepth = GOF_QUEUE_DEPTH;  // entries per lane; drained before a lane could overflow
 
+constexpr unsigned kQueueStride = kForceThreads * 4u;  // bytes between a lane's consecutive entries
 struct BoidQueue {
-    unsigned base;   // shared-memory address of this lane's entry 0 (entries kForceThreads * 4 bytes apart)
-    int count;
+    unsigned base;   // shared-memory address of this lane's entry 0 (entries kQueueStride bytes apart)
+    unsigned next;   // ... of its first free entry: a push is one predicated store and one predicated add
     float fx, fy, fz;  // force of the drained pairs so far, summed in queue order
 };
+
+__device__ __forceinline__ int queue_count(const BoidQueue& q) { return (int)((q.next - q.base) / kQueueStride); }
+#ifndef GOF_BOIDS_GROUP
+#define GOF_BOIDS_GROUP 10
+#endif
+constexpr int kBoidsGroup = GOF_BOIDS_GROUP;  // candidates tested per round of the Boids walk (run_pairs)
+static_assert(kBoidsGroup >= 1 && kBoidsGroup < kQueueDepth, "a round's notes must fit the queue");
+// (a warp vote on this triggers a drain: room for one more round of notes per lane is always kept)
+__device__ __forceinline__ bool queue_nearly_full(const BoidQueue& q)
+{
+    return q.next - q.base > (unsigned)(kQueueDepth - kBoidsGroup) * kQueueStride;
+}
 
 // An entry is the neighbour's slot and the periodic image of the run it was met in:
 // slot | packed shifts << 26 (at most 2^26 slots per engine while a species pair is Boids-kind).
@@ -372,19 +385,21 @@ constexpr int kQueueSlotBits = 26;
 
 __device__ __forceinline__ void queue_push(BoidQueue& q, unsigned entry, bool hit)
 {
-    if (hit) asm volatile("st.shared.b32 [%0], %1;" ::"r"(q.base + (unsigned)q.count * (kForceThreads * 4u)), "r"(entry));
-    q.count += hit ? 1 : 0;
+    if (hit) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(q.next), "r"(entry));
+        q.next += kQueueStride;
+    }
 }
 
 // Systems with Boids-kind pairs: the hot loop is nothing but the test and the note.
 template <bool LOWFIX>
 __device__ __forceinline__ void pair_note(const Geometry& g, const Image& im, const float4 pj, unsigned entry,
-                                          BoidQueue& q)
+                                          BoidQueue& q, bool live = true)
 {
     float dx = im.x - pj.x, dy = im.y - pj.y, dz = im.z - pj.z;
     if (LOWFIX) { dx += im.lx; dy += im.ly; dz += im.lz; }
     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    queue_push(q, entry, d2 < g.r2_hi && d2 > 1e-10f);
+    queue_push(q, entry, live && d2 < g.r2_hi && d2 > 1e-10f);
 }
 
 // Out of line (one copy: the hot loops stay small).  The entries of a lane are handled one after
@@ -435,10 +450,10 @@ __device__ __noinline__ float3 queue_drain(float3 f, unsigned qbase, int count, 
 __device__ __forceinline__ void drain(BoidQueue& q, const Home& h, const PairParam* __restrict__ tabrow,
                                       float* __restrict__ boid_acc, const ForceArgs& a, const Geometry& g)
 {
-    const float3 f = queue_drain(make_float3(q.fx, q.fy, q.fz), q.base, q.count, h.x, h.y, h.z,
+    const float3 f = queue_drain(make_float3(q.fx, q.fy, q.fz), q.base, queue_count(q), h.x, h.y, h.z,
                                  h.type, h.kinds, tabrow, boid_acc, a, g);
     q.fx = f.x; q.fy = f.y; q.fz = f.z;
-    q.count = 0;
+    q.next = q.base;
 }
 
 // Mixed systems (both kinds of pairs): distance test, then the interaction behind a branch.
@@ -480,18 +495,33 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
     float3 rep = make_float3(0.0f, 0.0f, 0.0f);
     const unsigned tag = (unsigned)im.shifts << kQueueSlotBits;
     int j = s;
+    if (KIND == kKindBoids) {
+        // Masked groups of kBoidsGroup candidates: every load of a group is in flight before the
+        // first test, and the last group of a run re-reads the run's last candidate and notes
+        // nothing for the slots past the end.  At three particles per cell a run is ~9 candidates:
+        // one round trip to L2 instead of the three of "two groups of four and a tail, one load at
+        // a time" (N = 4M: 1.26 -> 1.11 ms, flocked 2.71 -> 2.41 ms; groups of 4 / 6 / 8 / 12: 1.15 /
+        // 1.11 / 1.12 / 1.21 ms).  The kernel is bound by these round trips, not by instructions:
+        // a push of 2.75 instead of 7 instructions changed nothing.
+        constexpr int G = kBoidsGroup;
+        for (; j < e; j += G) {
+            float4 p[G];
+#pragma unroll
+            for (int k = 0; k < G; ++k) p[k] = ldg4(a.posw + min(j + k, e - 1));
+            const unsigned tj = tag + (unsigned)j;
+#pragma unroll
+            for (int k = 0; k < G; ++k) pair_note<LOWFIX>(g, im, p[k], tj + (unsigned)k, q, j + k < e);
+            // lanes drain together, each its own entries
+            if (__any_sync(__activemask(), queue_nearly_full(q))) drain(q, h, tabrow, boid_acc, a, g);
+        }
+        h.ax += ax0; h.ay += ay0; h.az += az0;
+        return;
+    }
     for (; j + 4 <= e; j += 4) {
         // four independent 16-byte loads issued ahead of the arithmetic that consumes them
         const float4 p0 = ldg4(a.posw + j), p1 = ldg4(a.posw + j + 1), p2 = ldg4(a.posw + j + 2),
                      p3 = ldg4(a.posw + j + 3);
-        if (KIND == kKindBoids) {
-            pair_note<LOWFIX>(g, im, p0, tag | (unsigned)j, q);
-            pair_note<LOWFIX>(g, im, p1, tag | (unsigned)(j + 1), q);
-            pair_note<LOWFIX>(g, im, p2, tag | (unsigned)(j + 2), q);
-            pair_note<LOWFIX>(g, im, p3, tag | (unsigned)(j + 3), q);
-            // lanes drain together, each its own entries
-            if (__any_sync(__activemask(), q.count > kQueueDepth - 4)) drain(q, h, tabrow, boid_acc, a, g);
-        } else if (KIND == kKindMixed) {
+        if (KIND == kKindMixed) {
             pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j, p0);
             pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j + 1, p1);
             pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j + 2, p2);
@@ -517,13 +547,8 @@ __device__ __forceinline__ void run_pairs(Home& h, RowAddr tabrow_s,
     }
     for (; j < e; ++j) {  // at most three
         const float4 pj = ldg4(a.posw + j);
-        if (KIND == kKindBoids) pair_note<LOWFIX>(g, im, pj, tag | (unsigned)j, q);
-        else if (KIND == kKindMixed) pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j, pj);
+        if (KIND == kKindMixed) pair_branchy<LOWFIX>(h, tabrow, boid_acc, a, g, im, j, pj);
         else if (needs_repair(g, pair_clusters<LOWFIX>(h, tabrow_s, g, im, pj))) repair(rep, h, tabrow, g, im, pj);
-    }
-    if (KIND == kKindBoids) {
-        // (the tail added at most three entries: room for the next group of four is kept here)
-        if (__any_sync(__activemask(), q.count > kQueueDepth - 4)) drain(q, h, tabrow, boid_acc, a, g);
     }
     if (KIND == kKindClusters) { h.ax += rep.x; h.ay += rep.y; h.az += rep.z; }
     h.ax += ax0; h.ay += ay0; h.az += az0;
@@ -1444,7 +1469,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
     }
     BoidQueue queue;
     queue.base = 0u;
-    queue.count = 0;
+    queue.next = 0u;
     queue.fx = queue.fy = queue.fz = 0.0f;
     if (BOIDS) {
         for (int q = 0; q < T; ++q) {
@@ -1454,6 +1479,7 @@ k_force(const __grid_constant__ Geometry g, const __grid_constant__ ForceArgs a)
         // the queue sits behind the per-type sums; entry k of this lane at base + k * 512
         queue.base = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float*>(behind) + T * kBoidSlots * kForceThreads +
                                                         threadIdx.x);
+        queue.next = queue.base;
     }
     __syncthreads();
 
